@@ -1,0 +1,462 @@
+// K3: flash-style cross-attention of the object queries over the BEV ++ image tokens on the
+// 5th-gen tensor cores (head dim 32, bf16 operands, fp32 accumulate / softmax statistics).
+//
+// Replaces flash_attn_unpadded_kvpacked_func as called from
+// projects/mmdet3d_plugin/models/utils/attention.py:46-92 (softmax(QK^T/sqrt(d))V, non-causal).
+//
+// Work decomposition.  An "item" is (frame b, head h, block of 256 queries); it needs
+// T = ceil(n_tokens/128) KV tile-steps.  The flat space items x T is cut into gridDim.x equal
+// contiguous ranges (stream-K), one persistent CTA per SM, so that any batch size fills all 148
+// SMs; every (item, CTA) overlap ("segment") writes a normalised fp32 partial + log2-sum-exp into
+// the workspace and a second kernel merges the segments of each item.  The same partial/LSE
+// algebra serves the multi-GPU KV-token split (cmt_lse_merge).
+//
+// CTA layout (384 threads):
+//   warps 0-3   softmax warpgroup 0 : owns query rows   0..127 of the block (TMEM lanes = rows)
+//   warps 4-7   softmax warpgroup 1 : owns query rows 128..255
+//   warp  8     TMA producer        : Q (64B swizzle), K tiles [128 tok x 32] (64B swizzle),
+//                                     V^T tiles [32 x 128 tok] (two 128B-swizzle boxes), 4-stage rings
+//   warp  9     MMA issuer          : S_i = Q_i K^T  (tcgen05.mma SS, M128 N128 K16 x2)
+//                                     O_i += P_i V   (tcgen05.mma TS, A = P in TMEM, M128 N32 K16 x8)
+//   warp 10     TMEM allocator
+// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,416) O1 [416,448).
+//
+// Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
+// rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
+// than 2^8, so the common tile does no accumulator traffic at all.
+#include "kernels.cuh"
+
+namespace cmt {
+
+namespace attn {
+constexpr int QBLK = 256;
+constexpr int KT = 128;
+constexpr int NK = 4, NV = 4;
+constexpr int TILE_BYTES = 128 * 32 * 2;  // 8 KB: one Q tile, one K tile, one V^T tile
+constexpr int THREADS = 384;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+constexpr int OFF_V = OFF_K + NK * TILE_BYTES;
+constexpr int OFF_BAR = OFF_V + NV * TILE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+}  // namespace attn
+
+struct TcAttnParams {
+    int B, H, Nq;
+    int kv_begin, kv_end;
+    int T;            // KV tile-steps per item
+    int qblocks;      // ceil(Nq / 256)
+    long long W;      // items * T
+    int S_max;        // partial slots per item
+    float* part_o;    // [items*S_max][256][32]
+    float* part_lse;  // [items*S_max][256]   (log2 domain)
+};
+
+__device__ __forceinline__ long long range_start(long long c, long long W, long long G) {
+    return (c * W) / G;
+}
+__device__ __forceinline__ int cta_of(long long x, long long W, long long G) {
+    return static_cast<int>(((x + 1) * G + W - 1) / W - 1);
+}
+
+__global__ void __launch_bounds__(attn::THREADS, 1)
+tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+               const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
+    using namespace attn;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* k_full = bars + 2;             // [NK]
+    uint64_t* k_empty = bars + 2 + NK;       // [NK]
+    uint64_t* v_full = bars + 2 + 2 * NK;    // [NV]
+    uint64_t* v_empty = v_full + NV;         // [NV]
+    uint64_t* s_full = v_empty + NV;         // [2]
+    uint64_t* p_full = s_full + 2;           // [2]
+    uint64_t* o_full = p_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_v);
+    }
+    if (warp == 9 && lane == 0) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < NK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 10) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long G = gridDim.x;
+    const long long pos_begin = range_start(blockIdx.x, p.W, G);
+    const long long pos_end = range_start(blockIdx.x + 1, p.W, G);
+
+    if (warp >= 8) {
+        setmaxnreg_dec<80>();
+        if (warp == 8 && lane == 0) {
+            // ----------------------------- TMA producer -----------------------------
+            uint32_t kc = 0, vc = 0, seg = 0;
+            for (long long pos = pos_begin; pos < pos_end;) {
+                const int item = static_cast<int>(pos / p.T);
+                const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+                const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+                const int qb = item % p.qblocks;
+                const int h = (item / p.qblocks) % p.H;
+                const int b = item / (p.qblocks * p.H);
+                mbar_wait(q_empty, (seg & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+                tma_load_4d(smem + OFF_Q, &tma_q, q_full, 0, qb * QBLK, h, b);
+                tma_load_4d(smem + OFF_Q + TILE_BYTES, &tma_q, q_full, 0, qb * QBLK + 128, h, b);
+                for (int jj = 0; jj < n; ++jj) {
+                    const int tok0 = p.kv_begin + (j0 + jj) * KT;
+                    const uint32_t ks = kc % NK, vs = vc % NV;
+                    mbar_wait(&k_empty[ks], ((kc / NK) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+                    tma_load_4d(smem + OFF_K + ks * TILE_BYTES, &tma_k, &k_full[ks], 0, tok0, h, b);
+                    ++kc;
+                    mbar_wait(&v_empty[vs], ((vc / NV) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                    uint8_t* sv = smem + OFF_V + vs * TILE_BYTES;
+                    tma_load_4d(sv, &tma_v, &v_full[vs], tok0, 0, h, b);
+                    tma_load_4d(sv + TILE_BYTES / 2, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
+                    ++vc;
+                }
+                pos += n;
+                ++seg;
+            }
+        } else if (warp == 9 && lane == 0) {
+            // ------------------------------ MMA issuer ------------------------------
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
+            const uint32_t sq = smem_u32(smem + OFF_Q);
+            uint32_t kc = 0, vc = 0, seg = 0;
+            uint32_t p_cnt[2] = {0, 0};
+            for (long long pos = pos_begin; pos < pos_end;) {
+                const int item = static_cast<int>(pos / p.T);
+                const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+                const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+                mbar_wait(q_full, seg & 1);
+                {
+                    const uint32_t ks = kc % NK;
+                    mbar_wait(&k_full[ks], (kc / NK) & 1);
+                    tc_fence_after();
+                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                        tc_commit(&s_full[i]);
+                    }
+                    tc_commit(&k_empty[ks]);
+                    ++kc;
+                    if (n == 1) tc_commit(q_empty);
+                }
+                for (int jj = 0; jj < n; ++jj) {
+                    const bool has_next = (jj + 1 < n);
+                    const uint32_t vs = vc % NV;
+                    mbar_wait(&v_full[vs], (vc / NV) & 1);
+                    const uint32_t ks = kc % NK;
+                    if (has_next) mbar_wait(&k_full[ks], (kc / NK) & 1);
+                    tc_fence_after();
+                    const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * TILE_BYTES), 128);
+                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        mbar_wait(&p_full[i], p_cnt[i] & 1);
+                        ++p_cnt[i];
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint64_t vd = vdesc + (((kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32) >> 4);
+                            tc_mma_ts(tmem_base + COL_O + i * 32, tmem_base + COL_P + i * 64 + kk * 8, vd,
+                                      idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        if (has_next) {
+                            const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                            tc_commit(&s_full[i]);
+                        } else {
+                            tc_commit(&o_full[i]);
+                        }
+                    }
+                    tc_commit(&v_empty[vs]);
+                    ++vc;
+                    if (has_next) {
+                        tc_commit(&k_empty[ks]);
+                        ++kc;
+                        if (jj + 2 == n) tc_commit(q_empty);
+                    }
+                }
+                pos += n;
+                ++seg;
+            }
+        }
+    } else {
+        // --------------------------- softmax warpgroups ---------------------------
+        setmaxnreg_inc<200>();
+        const int wg = warp >> 2;                       // 0 or 1 -> Q tile
+        const int r = (warp & 3) * 32 + lane;           // row inside the 128-row tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_base + COL_S + wg * 128;
+        const uint32_t t_p = tmem_base + lane_base + COL_P + wg * 64;
+        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
+        uint32_t tile_cnt = 0, seg = 0;
+        for (long long pos = pos_begin; pos < pos_end;) {
+            const int item = static_cast<int>(pos / p.T);
+            const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+            const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            float m = -INFINITY, l = 0.0f;
+            for (int jj = 0; jj < n; ++jj) {
+                mbar_wait(&s_full[wg], tile_cnt & 1);
+                ++tile_cnt;
+                tc_fence_after();
+                uint32_t s[4][32];
+                tmem_ld32(t_s + 0, s[0]);
+                tmem_ld32(t_s + 32, s[1]);
+                tmem_ld32(t_s + 64, s[2]);
+                tmem_ld32(t_s + 96, s[3]);
+                tc_wait_ld();
+                const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
+                if (valid < KT) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[2][i]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (jj == 0) {
+                    m = mx;  // O_i is overwritten by the first PV of the segment: nothing to rescale
+                } else {
+                    const bool need = (mx - m) > RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float m_new = need ? mx : m;
+                        const float alpha = ex2_approx(m - m_new);
+                        l *= alpha;
+                        uint32_t o[32];
+                        tmem_ld32(t_o, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_o, o);
+                        m = m_new;
+                    }
+                }
+                float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m);
+                        const float e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m);
+                        l0 += e0;
+                        l1 += e1;
+                        pk[i] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st16(t_p + c * 16, pk);
+                }
+                l += l0 + l1;
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[wg]);
+            }
+            // segment epilogue: normalised partial + log2-sum-exp into the workspace
+            mbar_wait(&o_full[wg], seg & 1);
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld32(t_o, o);
+            tc_wait_ld();
+            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(static_cast<long long>(item) * p.T, p.W, G));
+            const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
+            const float inv = 1.0f / l;
+            float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
+                                     __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
+            p.part_lse[prow] = m + log2f(l);
+            tc_fence_before();
+            pos += n;
+            ++seg;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 10) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Merge the per-CTA segments of each item.  One thread = (item row, 4 output dims).
+template <bool kBf16>
+__global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long long G, void* o,
+                                                            float* lse) {
+    const long long items = static_cast<long long>(p.B) * p.H * p.qblocks;
+    const long long total = items * attn::QBLK * 8;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int q4 = static_cast<int>(t & 7);
+        const int rr = static_cast<int>((t >> 3) % attn::QBLK);
+        const int item = static_cast<int>((t >> 3) / attn::QBLK);
+        const int qb = item % p.qblocks;
+        const int h = (item / p.qblocks) % p.H;
+        const int b = item / (p.qblocks * p.H);
+        const int row = qb * attn::QBLK + rr;
+        if (row >= p.Nq) continue;
+        const long long x0 = static_cast<long long>(item) * p.T;
+        const int nseg = cta_of(x0 + p.T - 1, p.W, G) - cta_of(x0, p.W, G) + 1;
+        float mx = -INFINITY;
+        for (int s = 0; s < nseg; ++s)
+            mx = fmaxf(mx, p.part_lse[(static_cast<long long>(item) * p.S_max + s) * attn::QBLK + rr]);
+        float den = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < nseg; ++s) {
+            const long long prow = (static_cast<long long>(item) * p.S_max + s) * attn::QBLK + rr;
+            const float w = exp2f(p.part_lse[prow] - mx);
+            den += w;
+            const float4 x = reinterpret_cast<const float4*>(p.part_o + prow * 32)[q4];
+            acc.x = fmaf(w, x.x, acc.x);
+            acc.y = fmaf(w, x.y, acc.y);
+            acc.z = fmaf(w, x.z, acc.z);
+            acc.w = fmaf(w, x.w, acc.w);
+        }
+        const float inv = 1.0f / den;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        const long long oidx = ((static_cast<long long>(b) * p.Nq + row) * p.H + h) * 8 + q4;  // float4 units
+        if (kBf16) {
+            uint2 w;
+            w.x = pack_bf16x2(acc.x, acc.y);
+            w.y = pack_bf16x2(acc.z, acc.w);
+            reinterpret_cast<uint2*>(o)[oidx] = w;
+        } else {
+            reinterpret_cast<float4*>(o)[oidx] = acc;
+        }
+        if (lse != nullptr && q4 == 0)
+            lse[(static_cast<long long>(b) * p.H + h) * p.Nq + row] = (mx + log2f(den)) * 0.6931471805599453f;
+    }
+}
+
+static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid) {
+    p->qblocks = (Nq + attn::QBLK - 1) / attn::QBLK;
+    p->T = (n_tok + attn::KT - 1) / attn::KT;
+    const long long items = static_cast<long long>(B) * H * p->qblocks;
+    p->W = items * p->T;
+    long long G = sms;
+    if (G > p->W) G = p->W;
+    if (G < 1) G = 1;
+    const long long chunk_min = p->W / G;  // >= 1
+    p->S_max = static_cast<int>((p->T - 1) / chunk_min + 2);
+    *grid = static_cast<int>(G);
+}
+
+size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
+    if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
+    TcAttnParams p{};
+    int grid;
+    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid);
+    const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
+    return slots * attn::QBLK * 33 * sizeof(float) + 256;
+}
+
+int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    using namespace attn;
+    const int n_tok = a.kv_end - a.kv_begin;
+    CMT_CHECK_ARG(n_tok > 0, "cmt_cross_attn_fwd: empty token range");
+    CMT_CHECK_ARG(a.q_ld % 8 == 0 && a.v_ld % 8 == 0 && a.k_bstride % 8 == 0 && a.k_hstride % 8 == 0 &&
+                      a.v_bstride % 8 == 0 && a.v_hstride % 8 == 0,
+                  "cmt_cross_attn_fwd(bf16): strides must be multiples of 8 elements");
+    CMT_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) |
+                    reinterpret_cast<uintptr_t>(a.vt) | reinterpret_cast<uintptr_t>(a.o)) & 15) == 0,
+                  "cmt_cross_attn_fwd(bf16): pointers must be 16-byte aligned");
+    TcAttnParams p{};
+    int grid;
+    attn_plan(a.B, a.H, a.Nq, n_tok, device_sm_count(), &p, &grid);
+    p.B = a.B;
+    p.H = a.H;
+    p.Nq = a.Nq;
+    p.kv_begin = a.kv_begin;
+    p.kv_end = a.kv_end;
+    const size_t need = tc_attn_workspace_bytes(a.B, a.H, a.Nq, n_tok);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("cmt_cross_attn_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return CMT_ERR_WORKSPACE;
+    }
+    const size_t slots = static_cast<size_t>(a.B) * a.H * p.qblocks * p.S_max;
+    uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    p.part_o = reinterpret_cast<float*>(wsp);
+    p.part_lse = p.part_o + slots * QBLK * 32;
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn)");
+        attr_done = true;
+    }
+    CUtensorMap tq, tk, tv;
+    {
+        uint64_t dims[4] = {32, static_cast<uint64_t>(a.Nq), static_cast<uint64_t>(a.H), static_cast<uint64_t>(a.B)};
+        uint64_t strides[3] = {static_cast<uint64_t>(a.q_ld) * 2, 64, static_cast<uint64_t>(a.Nq) * a.q_ld * 2};
+        uint32_t box[4] = {32, 128, 1, 1};
+        int rc = encode_tma_bf16(&tq, a.q, 4, dims, strides, box, 64);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {32, static_cast<uint64_t>(a.kv_end), static_cast<uint64_t>(a.H), static_cast<uint64_t>(a.B)};
+        uint64_t strides[3] = {64, static_cast<uint64_t>(a.k_hstride) * 2, static_cast<uint64_t>(a.k_bstride) * 2};
+        uint32_t box[4] = {32, KT, 1, 1};
+        int rc = encode_tma_bf16(&tk, a.k, 4, dims, strides, box, 64);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(a.kv_end), 32, static_cast<uint64_t>(a.H), static_cast<uint64_t>(a.B)};
+        uint64_t strides[3] = {static_cast<uint64_t>(a.v_ld) * 2, static_cast<uint64_t>(a.v_hstride) * 2,
+                               static_cast<uint64_t>(a.v_bstride) * 2};
+        uint32_t box[4] = {64, 32, 1, 1};
+        int rc = encode_tma_bf16(&tv, a.vt, 4, dims, strides, box, 128);
+        if (rc) return rc;
+    }
+    tc_attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
+    const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * QBLK * 8;
+    long long mblocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(device_sm_count()) * 8;
+    if (mblocks > cap) mblocks = cap;
+    if (a.o_bf16)
+        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
+    else
+        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
+    CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(merge)");
+    return CMT_OK;
+}
+
+}  // namespace cmt

@@ -1,0 +1,264 @@
+// extern "C" surface of libcmtcoop_b200 (see include/cmtcoop_b200.h for the contract of every
+// entry point and the reference file:line each one replaces).
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "kernels.cuh"
+
+namespace cmt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: CUDA error %d (%s)", what, static_cast<int>(e), cudaGetErrorString(e));
+    return CMT_ERR_CUDA;
+}
+
+struct DevInfo {
+    int sms = 0;
+    int major = 0, minor = 0;
+    bool ok = false;
+};
+static DevInfo g_dev[64];
+static std::once_flag g_dev_once[64];
+
+static const DevInfo& dev_info() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::call_once(g_dev_once[dev], [dev]() {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+            g_dev[dev].sms = prop.multiProcessorCount;
+            g_dev[dev].major = prop.major;
+            g_dev[dev].minor = prop.minor;
+            g_dev[dev].ok = true;
+        }
+    });
+    return g_dev[dev];
+}
+
+int device_sm_count() {
+    const DevInfo& d = dev_info();
+    return d.sms > 0 ? d.sms : 148;
+}
+
+int require_sm100() {
+    const DevInfo& d = dev_info();
+    if (!d.ok) {
+        set_error("no CUDA device available (libcmtcoop_b200 has no CPU fallback)");
+        return CMT_ERR_ARCH;
+    }
+    if (d.major != 10) {
+        set_error("libcmtcoop_b200 requires an sm_100 (B200) device, found sm_%d%d; there is no fallback path",
+                  d.major, d.minor);
+        return CMT_ERR_ARCH;
+    }
+    return CMT_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int encode_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    std::call_once(g_encode_once, []() {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+    if (!g_encode) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return CMT_ERR_CUDA;
+    }
+    cuuint64_t gdims[5];
+    cuuint64_t gstrides[4];
+    cuuint32_t gbox[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+        if (i < rank - 1) gstrides[i] = strides_bytes[i];
+    }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                        : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                          const_cast<void*>(base), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu, stride0 %llu)",
+                  static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides_bytes[0]);
+        return CMT_ERR_CUDA;
+    }
+    return CMT_OK;
+}
+
+}  // namespace cmt
+
+using namespace cmt;
+
+#define CMT_REQUIRE_DEVICE()            \
+    do {                                \
+        int rc__ = require_sm100();     \
+        if (rc__ != CMT_OK) return rc__; \
+    } while (0)
+
+extern "C" {
+
+int cmt_version(void) { return 100; }
+
+const char* cmt_last_error_string(void) { return g_err; }
+
+int cmt_check_device(int dev) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cmt_check_device: no CUDA device %d (%s)", dev, cudaGetErrorString(e));
+        return CMT_ERR_ARCH;
+    }
+    if (prop.major != 10) {
+        set_error("cmt_check_device: device %d is sm_%d%d, sm_100 required", dev, prop.major, prop.minor);
+        return CMT_ERR_ARCH;
+    }
+    return CMT_OK;
+}
+
+int cmt_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, int D, float pad_h, float pad_w,
+               const float* pc_range_host, int out_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_ray_pe(img2lidar, out, n_cam, H, W, D, pad_h, pad_w, pc_range_host, out_dtype,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int cmt_ray_query_pe(const float* ref, const float* lidar2img, const float* img2lidar, void* out, float* mask,
+                     int B, int V, int Nq, int D, float pad_h, float pad_w, const float* pc_range_host,
+                     int out_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_ray_query_pe(ref, lidar2img, img2lidar, out, mask, B, V, Nq, D, pad_h, pad_w, pc_range_host,
+                               out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq, int C,
+                        int emb_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_masked_view_sum(emb, mask, out, B, V, Nq, C, emb_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_pos2embed(pos, out, N, pos_stride, F, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos, const float* rv_pos,
+                      void* xk, void* xv, int B, int C, int n_bev, int V, int n_img, int out_dtype,
+                      void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_gather_tokens(x_bev, x_img, bev_pos, rv_pos, xk, xv, B, C, n_bev, V, n_img, out_dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
+                      int64_t lda, int64_t ldb, int64_t ldc, int64_t cb, int64_t cb_stride, int batch,
+                      int64_t strideA, int64_t strideB, int64_t strideC, float alpha, int flags, int in_dtype,
+                      int out_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    CMT_CHECK_ARG(A && B && C, "cmt_gemm_bias_act: null pointer");
+    CMT_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "cmt_gemm_bias_act: bad shape M=%d N=%d K=%d batch=%d", M,
+                  N, K, batch);
+    CMT_CHECK_ARG(lda >= K && ldb >= K && cb > 0, "cmt_gemm_bias_act: bad leading dimensions");
+    CMT_CHECK_ARG(in_dtype == CMT_F32 || in_dtype == CMT_BF16, "cmt_gemm_bias_act: bad in_dtype");
+    CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gemm_bias_act: bad out_dtype");
+    GemmArgs g{};
+    g.A = A;
+    g.B = B;
+    g.bias = bias;
+    g.C = C;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.lda = lda;
+    g.ldb = ldb;
+    g.ldc = ldc;
+    g.cb = cb;
+    g.cb_stride = cb_stride;
+    g.strideA = strideA;
+    g.strideB = strideB;
+    g.strideC = strideC;
+    g.alpha = alpha;
+    g.relu = (flags & CMT_GEMM_RELU) ? 1 : 0;
+    g.bias_per_row = (flags & CMT_GEMM_BIAS_PER_ROW) ? 1 : 0;
+    g.out_bf16 = out_dtype == CMT_BF16;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (in_dtype == CMT_BF16 && !(flags & CMT_GEMM_FORCE_SIMT)) return launch_tc_gemm(g, batch, s);
+    return launch_simt_gemm(g, batch, in_dtype, s);
+}
+
+size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
+    return tc_attn_workspace_bytes(B, H, Nq, n_kv_tokens);
+}
+
+int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int H, int Nq,
+                       int N_kv, int kv_begin, int kv_end, int64_t q_ld, int64_t k_bstride, int64_t k_hstride,
+                       int64_t v_bstride, int64_t v_hstride, int64_t v_ld, int dtype, int o_dtype,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    CMT_CHECK_ARG(q && k && vt && o, "cmt_cross_attn_fwd: null pointer");
+    CMT_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && N_kv > 0, "cmt_cross_attn_fwd: bad shape");
+    CMT_CHECK_ARG(0 <= kv_begin && kv_begin < kv_end && kv_end <= N_kv,
+                  "cmt_cross_attn_fwd: bad token range [%d,%d) of %d", kv_begin, kv_end, N_kv);
+    CMT_CHECK_ARG(dtype == CMT_F32 || dtype == CMT_BF16 || dtype == CMT_BF16_SIMT, "cmt_cross_attn_fwd: bad dtype");
+    CMT_CHECK_ARG(o_dtype == CMT_F32 || o_dtype == CMT_BF16, "cmt_cross_attn_fwd: bad o_dtype");
+    CMT_CHECK_ARG(q_ld >= H * 32 && v_ld >= kv_end, "cmt_cross_attn_fwd: bad leading dimensions");
+    AttnArgs a{};
+    a.q = q;
+    a.k = k;
+    a.vt = vt;
+    a.o = o;
+    a.lse = lse;
+    a.B = B;
+    a.H = H;
+    a.Nq = Nq;
+    a.N_kv = N_kv;
+    a.kv_begin = kv_begin;
+    a.kv_end = kv_end;
+    a.q_ld = q_ld;
+    a.k_bstride = k_bstride;
+    a.k_hstride = k_hstride;
+    a.v_bstride = v_bstride;
+    a.v_hstride = v_hstride;
+    a.v_ld = v_ld;
+    a.o_bf16 = o_dtype == CMT_BF16;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CMT_BF16) return launch_tc_attn(a, workspace, workspace_bytes, s);
+    return launch_simt_attn(a, dtype == CMT_BF16_SIMT ? CMT_BF16 : dtype, s);
+}
+
+int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B, int H,
+                  int Nq, int o_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_lse_merge(o_parts, lse_parts, o, lse, G, B, H, Nq, o_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_coop_max(a, b, out, n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// K4 token gather (NCHW fp32 -> token-major, BEV ++ image concat, +pos, cast), the V2I
+// element-wise max merge, and the log-sum-exp merge of attention partials.  HBM bound.
+//
+// Reference arithmetic followed (never copied):
+//   gather : models/utils/cmt_transformer.py:105-110 + models/utils/petr_transformer.py:296-299
+//   coop   : models/dense_heads/cmt_head_coop.py:358,383-389
+#include "kernels.cuh"
+
+namespace cmt {
+
+constexpr int kTileTok = 32;
+
+// Block = one tile of 32 consecutive tokens of one source map (the BEV map of frame b, or one
+// camera of frame b) x all C channels.  Phase 1 reads channel rows (128 contiguous bytes per
+// warp load) into a transposed smem tile [token][channel] (row pitch C+1 words -> conflict-free
+// writes); phase 2 lets each warp emit whole token rows (C contiguous elements) for xk and xv.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) gather_tokens_kernel(
+    const float* __restrict__ x_bev, const float* __restrict__ x_img,
+    const float* __restrict__ bev_pos, const float* __restrict__ rv_pos, void* __restrict__ xk,
+    void* __restrict__ xv, int C, int n_bev, int V, int n_img, int tiles_bev, int tiles_img) {
+    extern __shared__ float tile[];  // [kTileTok][C + 1]
+    const int b = blockIdx.y;
+    const int pitch = C + 1;
+    int tix = blockIdx.x;
+    const float* src;       // [C, n_src] channel-major
+    const float* pos;       // [n_src, C] token-major (already offset to this source's first token)
+    int n_src, t0;
+    long long dst_tok0;     // first destination token of this source inside the frame
+    if (tix < tiles_bev) {
+        src = x_bev + static_cast<long long>(b) * C * n_bev;
+        pos = bev_pos;
+        n_src = n_bev;
+        t0 = tix * kTileTok;
+        dst_tok0 = 0;
+    } else {
+        tix -= tiles_bev;
+        const int v = tix / tiles_img;
+        const int cam = b * V + v;
+        src = x_img + static_cast<long long>(cam) * C * n_img;
+        pos = rv_pos + static_cast<long long>(cam) * n_img * C;
+        n_src = n_img;
+        t0 = (tix % tiles_img) * kTileTok;
+        dst_tok0 = n_bev + static_cast<long long>(v) * n_img;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tok = t0 + lane;
+    const bool tok_ok = tok < n_src;
+    for (int c = warp; c < C; c += 8) {
+        const float val = tok_ok ? __ldg(src + static_cast<long long>(c) * n_src + tok) : 0.0f;
+        tile[lane * pitch + c] = val;
+    }
+    __syncthreads();
+    const long long N_kv = n_bev + static_cast<long long>(V) * n_img;
+    for (int r = warp; r < kTileTok; r += 8) {
+        const int st = t0 + r;
+        if (st >= n_src) break;
+        const long long drow = (static_cast<long long>(b) * N_kv + dst_tok0 + st) * C;
+        const float* prow = pos + static_cast<long long>(st) * C;
+        const float* trow = tile + r * pitch;
+        for (int c = lane * 2; c < C; c += 64) {
+            const float m0 = trow[c], m1 = trow[c + 1];
+            const float2 pp = *reinterpret_cast<const float2*>(prow + c);
+            if (kBf16) {
+                reinterpret_cast<uint32_t*>(xk)[(drow + c) >> 1] = pack_bf16x2(m0 + pp.x, m1 + pp.y);
+                reinterpret_cast<uint32_t*>(xv)[(drow + c) >> 1] = pack_bf16x2(m0, m1);
+            } else {
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(xk) + drow + c) =
+                    make_float2(m0 + pp.x, m1 + pp.y);
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(xv) + drow + c) =
+                    make_float2(m0, m1);
+            }
+        }
+    }
+}
+
+int launch_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+                         const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
+                         int n_img, int out_dtype, cudaStream_t stream) {
+    CMT_CHECK_ARG(xk && xv, "cmt_gather_tokens: null output");
+    CMT_CHECK_ARG(B > 0 && C > 0 && (C % 2) == 0, "cmt_gather_tokens: bad B/C");
+    CMT_CHECK_ARG(n_bev >= 0 && V >= 0 && n_img >= 0, "cmt_gather_tokens: bad token counts");
+    CMT_CHECK_ARG(n_bev == 0 || (x_bev && bev_pos), "cmt_gather_tokens: BEV pointers missing");
+    CMT_CHECK_ARG(V == 0 || n_img == 0 || (x_img && rv_pos), "cmt_gather_tokens: image pointers missing");
+    CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gather_tokens: bad dtype");
+    CMT_CHECK_ARG(B <= 65535, "cmt_gather_tokens: batch too large for one launch");
+    const int tiles_bev = (n_bev + kTileTok - 1) / kTileTok;
+    const int tiles_img = (n_img + kTileTok - 1) / kTileTok;
+    const int tiles = tiles_bev + V * tiles_img;
+    if (tiles == 0) return CMT_OK;
+    const size_t smem = static_cast<size_t>(kTileTok) * (C + 1) * sizeof(float);
+    CMT_CHECK_ARG(smem <= 48 * 1024, "cmt_gather_tokens: C too large (%d)", C);
+    dim3 grid(tiles, B);
+    if (out_dtype == CMT_BF16)
+        gather_tokens_kernel<true><<<grid, 256, smem, stream>>>(
+            x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, n_img, tiles_bev, tiles_img);
+    else
+        gather_tokens_kernel<false><<<grid, 256, smem, stream>>>(
+            x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, n_img, tiles_bev, tiles_img);
+    CMT_LAUNCH_CHECK("cmt_gather_tokens");
+    return CMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float nan_to_num(float x) {
+    if (x != x) return 0.0f;
+    if (x == __int_as_float(0x7f800000)) return 3.4028234663852886e38f;
+    if (x == __int_as_float(0xff800000)) return -3.4028234663852886e38f;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) coop_max_kernel(const float* __restrict__ a,
+                                                       const float* __restrict__ b,
+                                                       float* __restrict__ out, long long n) {
+    const long long n4 = n >> 2;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n4;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[t];
+        const float4 y = reinterpret_cast<const float4*>(b)[t];
+        float4 r;
+        r.x = fmaxf(nan_to_num(x.x), nan_to_num(y.x));
+        r.y = fmaxf(nan_to_num(x.y), nan_to_num(y.y));
+        r.z = fmaxf(nan_to_num(x.z), nan_to_num(y.z));
+        r.w = fmaxf(nan_to_num(x.w), nan_to_num(y.w));
+        reinterpret_cast<float4*>(out)[t] = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long t = (n4 << 2) + threadIdx.x;
+        out[t] = fmaxf(nan_to_num(a[t]), nan_to_num(b[t]));
+    }
+}
+
+int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream) {
+    CMT_CHECK_ARG(a && b && out && n >= 0, "cmt_coop_max: bad arguments");
+    CMT_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                    reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                  "cmt_coop_max: pointers must be 16-byte aligned");
+    if (n == 0) return CMT_OK;
+    long long blocks = ((n >> 2) + 255) / 256;
+    const long long cap = static_cast<long long>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    coop_max_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(a, b, out, n);
+    CMT_LAUNCH_CHECK("cmt_coop_max");
+    return CMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// o = sum_g exp(lse_g - lse) * o_g ,  lse = log(sum_g exp(lse_g)).  One thread per (b, n, h, 4 dims).
+template <bool kBf16>
+__global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ o_parts,
+                                                        const float* __restrict__ lse_parts,
+                                                        void* __restrict__ o,
+                                                        float* __restrict__ lse, int G, int B, int H,
+                                                        int Nq) {
+    const long long total = static_cast<long long>(B) * Nq * H * 8;
+    const long long part_o = static_cast<long long>(B) * Nq * H * 32;
+    const long long part_l = static_cast<long long>(B) * H * Nq;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int q4 = static_cast<int>(t & 7);
+        const int h = static_cast<int>((t >> 3) % H);
+        const int n = static_cast<int>(((t >> 3) / H) % Nq);
+        const int b = static_cast<int>((t >> 3) / (static_cast<long long>(H) * Nq));
+        const long long li = (static_cast<long long>(b) * H + h) * Nq + n;
+        float mx = -INFINITY;
+        for (int g = 0; g < G; ++g) mx = fmaxf(mx, lse_parts[g * part_l + li]);
+        float den = 0.0f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < G; ++g) {
+            const float l = lse_parts[g * part_l + li];
+            const float w = (l == -INFINITY) ? 0.0f : __expf(l - mx);
+            den += w;
+            const float4 x = reinterpret_cast<const float4*>(o_parts + g * part_o)[t];
+            acc.x = fmaf(w, x.x, acc.x);
+            acc.y = fmaf(w, x.y, acc.y);
+            acc.z = fmaf(w, x.z, acc.z);
+            acc.w = fmaf(w, x.w, acc.w);
+        }
+        const float inv = den > 0.0f ? 1.0f / den : 0.0f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        if (kBf16) {
+            uint2 w;
+            w.x = pack_bf16x2(acc.x, acc.y);
+            w.y = pack_bf16x2(acc.z, acc.w);
+            reinterpret_cast<uint2*>(o)[t] = w;
+        } else {
+            reinterpret_cast<float4*>(o)[t] = acc;
+        }
+        if (lse != nullptr && q4 == 0) lse[li] = mx + logf(den);
+    }
+}
+
+int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
+                     int B, int H, int Nq, int o_dtype, cudaStream_t stream) {
+    CMT_CHECK_ARG(o_parts && lse_parts && o, "cmt_lse_merge: null pointer");
+    CMT_CHECK_ARG(G > 0 && B > 0 && H > 0 && Nq > 0, "cmt_lse_merge: bad shape");
+    const long long total = static_cast<long long>(B) * Nq * H * 8;
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (o_dtype == CMT_BF16)
+        lse_merge_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(o_parts, lse_parts, o,
+                                                                            lse, G, B, H, Nq);
+    else if (o_dtype == CMT_F32)
+        lse_merge_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(o_parts, lse_parts, o,
+                                                                             lse, G, B, H, Nq);
+    else
+        CMT_CHECK_ARG(false, "cmt_lse_merge: bad dtype");
+    CMT_LAUNCH_CHECK("cmt_lse_merge");
+    return CMT_OK;
+}
+
+}  // namespace cmt

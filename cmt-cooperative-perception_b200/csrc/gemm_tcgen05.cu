@@ -1,0 +1,280 @@
+// K2: projection / MLP GEMM on the 5th-gen tensor cores.
+//
+//   C = act((A * B^T + bias) * alpha),  A:[M,K] bf16, B:[N,K] bf16 (both K-major), fp32 accumulate.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer  : 3-D tensor maps (K, rows, batch), 128B swizzle, 4-stage smem ring
+//   warp 1      MMA issuer    : one elected thread, tcgen05.mma cta_group::1 kind::f16,
+//                               M=128 x N=256 x K=16 per instruction, accumulator in TMEM
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, ping-pong)
+//   warps 4..7  epilogue      : tcgen05.ld 32x32b -> bias / alpha / ReLU -> bf16|fp32 -> global,
+//                               overlapped with the next tile's main loop
+//
+// Replaces F.linear in models/utils/attention.py:21-27,138 and the PE MLPs of
+// models/dense_heads/cmt_head.py:292-301 (reference runs them as fp32 cuBLAS SGEMMs).
+#include "kernels.cuh"
+
+namespace cmt {
+
+namespace gemm {
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+}  // namespace gemm
+
+struct TcGemmParams {
+    const float* bias;
+    void* C;
+    int M, N, K;
+    long long ldc, cb, cb_stride, strideC;
+    float alpha;
+    int relu, bias_per_row, out_bf16;
+    int a_batched, b_batched;
+    int m_tiles, n_tiles, total_tiles, num_kb;
+};
+
+__global__ void __launch_bounds__(gemm::THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const TcGemmParams p) {
+    using namespace gemm;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // ----------------------------- TMA producer -----------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_batch;
+                const int r = tile - z * tiles_per_batch;
+                const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
+                    tma_load_3d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_desc(sa, 128);
+                    const uint64_t bdesc = make_kmajor_desc(sa + A_BYTES, 128);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes per K=16 step inside the 128B swizzle atom (>>4 -> +2)
+                        tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------- epilogue -------------------------------
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int z = tile / tiles_per_batch;
+            const int r = tile - z * tiles_per_batch;
+            const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int m = mt * BM + quad * 32 + lane;
+            const bool m_ok = m < p.M;
+            const float row_bias = (p.bias && p.bias_per_row && m_ok) ? __ldg(p.bias + m) : 0.0f;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int n0 = nt * BN + c * 32;
+                if (n0 >= p.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(t_row + c * 32, v);
+                tc_wait_ld();
+                if (m_ok) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(v[i]);
+                        if (p.bias) x += p.bias_per_row ? row_bias : ((n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f);
+                        x *= p.alpha;
+                        if (p.relu) x = fmaxf(x, 0.0f);
+                        f[i] = x;
+                    }
+                    const long long off = z * p.strideC + (n0 / p.cb) * p.cb_stride +
+                                          static_cast<long long>(m) * p.ldc + (n0 % p.cb);
+                    const bool full = (n0 + 32 <= p.N);
+                    if (p.out_bf16) {
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 w;
+                                w.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                                w.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                                w.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                                w.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                                reinterpret_cast<uint4*>(dst)[i] = w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+                        }
+                    } else {
+                        float* dst = reinterpret_cast<float*>(p.C) + off;
+                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(dst)[i] =
+                                    make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < p.N) dst[i] = f[i];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
+    using namespace gemm;
+    CMT_CHECK_ARG(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0,
+                  "cmt_gemm_bias_act(bf16): K, lda, ldb must be multiples of 8 (K=%d lda=%lld ldb=%lld)",
+                  g.K, g.lda, g.ldb);
+    CMT_CHECK_ARG(((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) == 0,
+                  "cmt_gemm_bias_act(bf16): operands must be 16-byte aligned");
+    CMT_CHECK_ARG(g.cb >= g.N || g.cb % 32 == 0,
+                  "cmt_gemm_bias_act(bf16): column block must be >= N or a multiple of 32");
+    CMT_CHECK_ARG(g.strideA % 8 == 0 && g.strideB % 8 == 0, "cmt_gemm_bias_act(bf16): batch strides must be multiples of 8");
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm)");
+        attr_done = true;
+    }
+
+    CUtensorMap ta, tb;
+    {
+        const bool batched = g.strideA != 0 && batch > 1;
+        uint64_t dims[3] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.M),
+                            static_cast<uint64_t>(batched ? batch : 1)};
+        uint64_t strides[2] = {static_cast<uint64_t>(g.lda) * 2,
+                               static_cast<uint64_t>(batched ? g.strideA : (long long)g.M * g.lda) * 2};
+        uint32_t box[3] = {BK, BM, 1};
+        int rc = encode_tma_bf16(&ta, g.A, 3, dims, strides, box, 128);
+        if (rc) return rc;
+    }
+    {
+        const bool batched = g.strideB != 0 && batch > 1;
+        uint64_t dims[3] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.N),
+                            static_cast<uint64_t>(batched ? batch : 1)};
+        uint64_t strides[2] = {static_cast<uint64_t>(g.ldb) * 2,
+                               static_cast<uint64_t>(batched ? g.strideB : (long long)g.N * g.ldb) * 2};
+        uint32_t box[3] = {BK, BN, 1};
+        int rc = encode_tma_bf16(&tb, g.B, 3, dims, strides, box, 128);
+        if (rc) return rc;
+    }
+
+    TcGemmParams p{};
+    p.bias = g.bias;
+    p.C = g.C;
+    p.M = g.M;
+    p.N = g.N;
+    p.K = g.K;
+    p.ldc = g.ldc;
+    p.cb = g.cb;
+    p.cb_stride = g.cb_stride;
+    p.strideC = g.strideC;
+    p.alpha = g.alpha;
+    p.relu = g.relu;
+    p.bias_per_row = g.bias_per_row;
+    p.out_bf16 = g.out_bf16;
+    p.a_batched = (g.strideA != 0 && batch > 1) ? 1 : 0;
+    p.b_batched = (g.strideB != 0 && batch > 1) ? 1 : 0;
+    p.m_tiles = (g.M + BM - 1) / BM;
+    p.n_tiles = (g.N + BN - 1) / BN;
+    const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * batch;
+    CMT_CHECK_ARG(total < (1ll << 31), "cmt_gemm_bias_act(bf16): too many tiles");
+    p.total_tiles = static_cast<int>(total);
+    p.num_kb = (g.K + BK - 1) / BK;
+    int grid = device_sm_count();
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    CMT_LAUNCH_CHECK("cmt_gemm_bias_act(tcgen05)");
+    return CMT_OK;
+}
+
+}  // namespace cmt

@@ -1,0 +1,56 @@
+// Internal launch interface between capi.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace cmt {
+
+struct GemmArgs {
+    const void* A;
+    const void* B;
+    const float* bias;
+    void* C;
+    int M, N, K;
+    long long lda, ldb, ldc, cb, cb_stride;
+    long long strideA, strideB, strideC;
+    float alpha;
+    int relu, bias_per_row, out_bf16;
+};
+
+struct AttnArgs {
+    const void* q;
+    const void* k;
+    const void* vt;
+    void* o;
+    float* lse;
+    int B, H, Nq, N_kv, kv_begin, kv_end;
+    long long q_ld, k_bstride, k_hstride, v_bstride, v_hstride, v_ld;
+    int o_bf16;
+};
+
+// pe_kernels.cu
+int launch_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, int D, float pad_h,
+                  float pad_w, const float* pc, int out_dtype, cudaStream_t stream);
+int launch_ray_query_pe(const float* ref, const float* l2i, const float* i2l, void* out,
+                        float* mask, int B, int V, int Nq, int D, float pad_h, float pad_w,
+                        const float* pc, int out_dtype, cudaStream_t stream);
+int launch_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq,
+                           int C, int emb_dtype, cudaStream_t stream);
+int launch_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype,
+                     cudaStream_t stream);
+// gather_kernels.cu
+int launch_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+                         const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
+                         int n_img, int out_dtype, cudaStream_t stream);
+int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
+                     int B, int H, int Nq, int o_dtype, cudaStream_t stream);
+// simt_kernels.cu
+int launch_simt_gemm(const GemmArgs& g, int batch, int in_dtype, cudaStream_t stream);
+int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);
+// gemm_tcgen05.cu
+int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream);
+// attn_tcgen05.cu
+size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens);
+int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace cmt

@@ -1,0 +1,293 @@
+"""Torch-tensor front ends of the C-ABI operators (``include/cmtcoop_b200.h``).
+
+PyTorch is used for device memory and the current stream only; every computation below runs in
+``libcmtcoop_b200.so``.  All tensors must live on a CUDA (sm_100) device -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import CMT_BF16, CMT_BF16_SIMT, CMT_F32, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_RELU
+
+HEAD_DIM = 32
+LOG2E = 1.4426950408889634
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _dt(dtype) -> int:
+    if dtype == torch.float32:
+        return CMT_F32
+    if dtype == torch.bfloat16:
+        return CMT_BF16
+    raise TypeError(f"unsupported dtype {dtype} (fp32 or bf16 only)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CmtLibraryError(f"{name} must be a CUDA tensor: libcmtcoop_b200 has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _pc(pc_range):
+    return (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+
+
+# ------------------------------------------------------------------------------------------
+def ray_pe(img2lidar, H, W, depth_num, pad_h, pad_w, pc_range, out_dtype=torch.bfloat16):
+    """K1 (cmt_head.py:417-432). img2lidar [n_cam,4,4] fp32 -> [n_cam,H,W,depth_num*3]."""
+    m = _cuda(img2lidar, "img2lidar", torch.float32)
+    n_cam = m.shape[0]
+    out = torch.empty((n_cam, H, W, depth_num * 3), dtype=out_dtype, device=m.device)
+    lib = _lib.load()
+    with torch.cuda.device(m.device):
+        rc = lib.cmt_ray_pe(_ptr(m), _ptr(out), n_cam, H, W, depth_num, float(pad_h), float(pad_w),
+                            ctypes.cast(_pc(pc_range), ctypes.c_void_p), _dt(out_dtype), _stream(m))
+    _lib.check(rc, "cmt_ray_pe")
+    _count()
+    return out
+
+
+def ray_query_pe(ref, lidar2img, img2lidar, depth_num, pad_h, pad_w, pc_range, out_dtype=torch.bfloat16):
+    """K1b (cmt_head.py:439-464). ref [B,Nq,3], matrices [B,V,4,4] -> feat [B,V,Nq,D*3], mask [B,V,Nq]."""
+    ref = _cuda(ref, "ref", torch.float32)
+    l2i = _cuda(lidar2img, "lidar2img", torch.float32)
+    i2l = _cuda(img2lidar, "img2lidar", torch.float32)
+    B, Nq, _ = ref.shape
+    V = l2i.shape[1]
+    out = torch.empty((B, V, Nq, depth_num * 3), dtype=out_dtype, device=ref.device)
+    mask = torch.empty((B, V, Nq), dtype=torch.float32, device=ref.device)
+    lib = _lib.load()
+    with torch.cuda.device(ref.device):
+        rc = lib.cmt_ray_query_pe(_ptr(ref), _ptr(l2i), _ptr(i2l), _ptr(out), _ptr(mask), B, V, Nq, depth_num,
+                                  float(pad_h), float(pad_w), ctypes.cast(_pc(pc_range), ctypes.c_void_p),
+                                  _dt(out_dtype), _stream(ref))
+    _lib.check(rc, "cmt_ray_query_pe")
+    _count()
+    return out, mask
+
+
+def masked_view_sum(emb, mask):
+    """(emb * mask[..., None]).sum(1)  (cmt_head.py:466). emb [B,V,Nq,C] -> [B,Nq,C] fp32."""
+    emb = _cuda(emb, "emb")
+    mask = _cuda(mask, "mask", torch.float32)
+    B, V, Nq, C = emb.shape
+    out = torch.empty((B, Nq, C), dtype=torch.float32, device=emb.device)
+    lib = _lib.load()
+    with torch.cuda.device(emb.device):
+        rc = lib.cmt_masked_view_sum(_ptr(emb), _ptr(mask), _ptr(out), B, V, Nq, C, _dt(emb.dtype), _stream(emb))
+    _lib.check(rc, "cmt_masked_view_sum")
+    _count()
+    return out
+
+
+def pos2embed(pos, num_pos_feats=128, out_dtype=torch.bfloat16):
+    """pos2embed (cmt_head.py:40-50). pos [...,>=2] fp32 -> [..., 2*num_pos_feats]."""
+    pos = _cuda(pos, "pos", torch.float32)
+    lead = pos.shape[:-1]
+    stride = pos.shape[-1]
+    N = int(math.prod(lead))
+    out = torch.empty((*lead, 2 * num_pos_feats), dtype=out_dtype, device=pos.device)
+    lib = _lib.load()
+    with torch.cuda.device(pos.device):
+        rc = lib.cmt_pos2embed(_ptr(pos), _ptr(out), N, stride, num_pos_feats, _dt(out_dtype), _stream(pos))
+    _lib.check(rc, "cmt_pos2embed")
+    _count()
+    return out
+
+
+def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16):
+    """K4 (cmt_transformer.py:105-110 + petr_transformer.py:296-299).
+    x_bev [B,C,Hb,Wb] | None, x_img [B*V,C,h,w] | None, bev_pos [N_bev,C], rv_pos [B*V*h*w, C] (any
+    leading shape) -> xk = mem+pos, xv = mem, both [B,N_kv,C]."""
+    ref = x_bev if x_bev is not None else x_img
+    dev = ref.device
+    C = ref.shape[1]
+    n_bev = 0
+    n_img = 0
+    if x_bev is not None:
+        x_bev = _cuda(x_bev, "x_bev", torch.float32)
+        bev_pos = _cuda(bev_pos, "bev_pos", torch.float32)
+        n_bev = x_bev.shape[2] * x_bev.shape[3]
+        assert x_bev.shape[0] == B and bev_pos.numel() == n_bev * C
+    if x_img is not None:
+        x_img = _cuda(x_img, "x_img", torch.float32)
+        rv_pos = _cuda(rv_pos, "rv_pos", torch.float32)
+        n_img = x_img.shape[2] * x_img.shape[3]
+        assert x_img.shape[0] == B * V and rv_pos.numel() == B * V * n_img * C
+    else:
+        V = 0
+    N_kv = n_bev + V * n_img
+    xk = torch.empty((B, N_kv, C), dtype=out_dtype, device=dev)
+    xv = torch.empty((B, N_kv, C), dtype=out_dtype, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.cmt_gather_tokens(_ptr(x_bev), _ptr(x_img), _ptr(bev_pos), _ptr(rv_pos), _ptr(xk), _ptr(xv),
+                                   B, C, n_bev, V, n_img, _dt(out_dtype), _stream(ref))
+    _lib.check(rc, "cmt_gather_tokens")
+    _count()
+    return xk, xv
+
+
+def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=1, strideA=0, strideB=0,
+         strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False):
+    """Raw cmt_gemm_bias_act: C = act((A B^T + bias) * alpha) with column-block output addressing."""
+    A = _cuda(A, "A")
+    Bm = _cuda(Bm, "B", A.dtype)
+    C = _cuda(C, "C")
+    if bias is not None:
+        bias = _cuda(bias, "bias", torch.float32)
+    flags = (GEMM_RELU if relu else 0) | (GEMM_BIAS_PER_ROW if bias_per_row else 0) | (GEMM_FORCE_SIMT if force_simt else 0)
+    lib = _lib.load()
+    with torch.cuda.device(A.device):
+        rc = lib.cmt_gemm_bias_act(_ptr(A), _ptr(Bm), _ptr(bias), _ptr(C), M, N, K, lda, ldb, ldc,
+                                   cb if cb is not None else max(N, 1), cb_stride, batch, strideA, strideB, strideC,
+                                   float(alpha), flags, _dt(A.dtype), _dt(C.dtype), _stream(A))
+    _lib.check(rc, "cmt_gemm_bias_act")
+    _count()
+    return C
+
+
+def linear(x, weight, bias=None, *, relu=False, alpha=1.0, out_dtype=None, force_simt=False):
+    """act((x @ weight.T + bias) * alpha) -- F.linear replacement. x [..., K], weight [N, K]."""
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    gemm(x2, weight, bias, out, M, N, K, lda=K, ldb=K, ldc=N, alpha=alpha, relu=relu, force_simt=force_simt)
+    return out.reshape(*x.shape[:-1], N)
+
+
+def project_keys(xk, w, bias, n_layers, H, out=None):
+    """K = xk @ w.T + bias for all layers at once, written in the per-head attention layout.
+    xk [B,N_kv,C]; w [n_layers*H*32, C]; -> [B, n_layers, H, N_kv, 32]."""
+    B, N_kv, C = xk.shape
+    NO = w.shape[0]
+    assert NO == n_layers * H * HEAD_DIM
+    if out is None:
+        out = torch.empty((B, n_layers, H, N_kv, HEAD_DIM), dtype=xk.dtype, device=xk.device)
+    gemm(xk, w, bias, out, N_kv, NO, C, lda=C, ldb=C, ldc=HEAD_DIM, cb=HEAD_DIM, cb_stride=N_kv * HEAD_DIM,
+         batch=B, strideA=N_kv * C, strideB=0, strideC=n_layers * H * N_kv * HEAD_DIM)
+    return out
+
+
+def project_values_t(xv, w, bias, n_layers, H, out=None):
+    """V^T = w @ xv^T + bias[:,None] for all layers, token-contiguous: [B, n_layers, H, 32, ld] with
+    ld = N_kv rounded up to 8 (TMA row pitch must be a multiple of 16 bytes)."""
+    B, N_kv, C = xv.shape
+    NO = w.shape[0]
+    assert NO == n_layers * H * HEAD_DIM
+    ld = (N_kv + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((B, n_layers, H, HEAD_DIM, ld), dtype=xv.dtype, device=xv.device)
+    gemm(w, xv, bias, out, NO, N_kv, C, lda=C, ldb=C, ldc=ld, batch=B, strideA=0, strideB=N_kv * C,
+         strideC=NO * ld, bias_per_row=True)
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(dev, nbytes):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False):
+    """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
+    vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq])."""
+    q = _cuda(q, "q")
+    k = _cuda(k, "k", q.dtype)
+    vt = _cuda(vt, "vt", q.dtype)
+    B, Nq, HD = q.shape
+    H = HD // HEAD_DIM
+    _, L, Hk, N_kv, _ = k.shape
+    ld = vt.shape[-1]
+    assert Hk == H and vt.shape[:4] == (B, L, H, HEAD_DIM)
+    kv_end = N_kv if kv_end is None else kv_end
+    o_dtype = o_dtype or q.dtype
+    o = torch.empty((B, Nq, HD), dtype=o_dtype, device=q.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if return_lse else None
+    esz = q.element_size()
+    kp = ctypes.c_void_p(k.data_ptr() + layer * H * N_kv * HEAD_DIM * esz)
+    vp = ctypes.c_void_p(vt.data_ptr() + layer * H * HEAD_DIM * ld * esz)
+    lib = _lib.load()
+    dt = _dt(q.dtype)
+    if simt and dt == CMT_BF16:
+        dt = CMT_BF16_SIMT
+    ws, ws_bytes = None, 0
+    if dt == CMT_BF16:
+        with torch.cuda.device(q.device):
+            ws_bytes = int(lib.cmt_cross_attn_workspace_bytes(B, H, Nq, kv_end - kv_begin))
+        ws = _workspace(q.device, ws_bytes)
+    with torch.cuda.device(q.device):
+        rc = lib.cmt_cross_attn_fwd(_ptr(q), kp, vp, _ptr(o), _ptr(lse), B, H, Nq, N_kv, kv_begin, kv_end, HD,
+                                    L * H * N_kv * HEAD_DIM, N_kv * HEAD_DIM, L * H * HEAD_DIM * ld, HEAD_DIM * ld,
+                                    ld, dt, _dt(o_dtype), _ptr(ws), ws_bytes, _stream(q))
+    _lib.check(rc, "cmt_cross_attn_fwd")
+    _count(2 if dt == CMT_BF16 else 1)
+    return (o, lse) if return_lse else o
+
+
+def lse_merge(o_parts, lse_parts, o_dtype=torch.bfloat16):
+    """Merge G partial attention results: o_parts [G,B,Nq,H*32] fp32, lse_parts [G,B,H,Nq] fp32."""
+    o_parts = _cuda(o_parts, "o_parts", torch.float32)
+    lse_parts = _cuda(lse_parts, "lse_parts", torch.float32)
+    G, B, Nq, HD = o_parts.shape
+    H = HD // HEAD_DIM
+    o = torch.empty((B, Nq, HD), dtype=o_dtype, device=o_parts.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=o_parts.device)
+    lib = _lib.load()
+    with torch.cuda.device(o_parts.device):
+        rc = lib.cmt_lse_merge(_ptr(o_parts), _ptr(lse_parts), _ptr(o), _ptr(lse), G, B, H, Nq, _dt(o_dtype),
+                               _stream(o_parts))
+    _lib.check(rc, "cmt_lse_merge")
+    _count()
+    return o, lse
+
+
+def coop_max(a, b):
+    """max(nan_to_num(a), nan_to_num(b)) (cmt_head_coop.py:358,383-389)."""
+    a = _cuda(a, "a", torch.float32)
+    b = _cuda(b, "b", torch.float32)
+    assert a.shape == b.shape
+    out = torch.empty_like(a)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.cmt_coop_max(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream(a))
+    _lib.check(rc, "cmt_coop_max")
+    _count()
+    return out

@@ -1,0 +1,375 @@
+"""CmtHead / CmtImageHead / CmtLidarHead and SeparateTaskHead with the reference's class names,
+constructor arguments, forward signatures and state-dict keys
+(projects/mmdet3d_plugin/models/dense_heads/cmt_head.py:97-1085), inference path only.
+
+What runs where:
+  * camera-ray PE lift, re-projection of the reference points, sine/cosine embedding, masked view
+    sum, token gather, every PE-MLP / projection GEMM and the cross-attention: libcmtcoop_b200.
+  * shared_conv (cuDNN), self-attention / LayerNorm / FFN over the 900 queries, the grouped Conv1d
+    task heads: torch CUDA ops ("next" rows).
+Losses, denoising queries and target assignment are training-only and not part of this package.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .bbox_coder import build_bbox_coder
+from .registry import HEADS, TRANSFORMER, ConfigDict
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    """mmdet.models.utils.transformer.inverse_sigmoid (mmdet 2.28.2)."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def multi_apply(func, *args, **kwargs):
+    """mmdet.core.multi_apply."""
+    from functools import partial
+    pfunc = partial(func, **kwargs) if kwargs else func
+    return tuple(map(list, zip(*map(pfunc, *args))))
+
+
+def pos2embed(pos, num_pos_feats=128, temperature=10000, out_dtype=torch.float32):
+    """cmt_head.py:40-50 on the GPU (cmt_pos2embed); `temperature` is accepted and unused, as there."""
+    return ops.pos2embed(pos.float().contiguous(), num_pos_feats, out_dtype=out_dtype)
+
+
+class GroupLayerNorm1d(nn.Module):
+    """cmt_head.py:53-94 (forward only)."""
+
+    def __init__(self, channels, groups=1, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+        self.groups = groups
+        self.eps = eps
+
+    def forward(self, x):
+        N, C, L = x.shape
+        xg = x.view(N, self.groups, C // self.groups, L)
+        mu = xg.mean(2, keepdim=True)
+        var = (xg - mu).pow(2).mean(2, keepdim=True)
+        y = (xg - mu) / (var + self.eps).sqrt()
+        return self.weight.view(1, C, 1) * y.view(N, C, L) + self.bias.view(1, C, 1)
+
+
+@HEADS.register_module()
+class SeparateTaskHead(nn.Module):
+    """cmt_head.py:97-203: per output name, grouped Conv1d -> group LN -> ReLU -> grouped Conv1d over the
+    query axis, one group per decoder layer."""
+
+    def __init__(self, in_channels, heads, groups=1, head_conv=64, final_kernel=1, init_bias=-2.19,
+                 init_cfg=None, **kwargs):
+        assert init_cfg is None
+        super().__init__()
+        self.heads = heads
+        self.groups = groups
+        self.init_bias = init_bias
+        for head in self.heads:
+            classes, num_conv = self.heads[head]
+            layers, c_in = [], in_channels
+            for _ in range(num_conv - 1):
+                layers += [nn.Conv1d(c_in * groups, head_conv * groups, kernel_size=final_kernel, stride=1,
+                                     padding=final_kernel // 2, groups=groups, bias=False),
+                           GroupLayerNorm1d(head_conv * groups, groups=groups), nn.ReLU(inplace=True)]
+                c_in = head_conv
+            layers.append(nn.Conv1d(head_conv * groups, classes * groups, kernel_size=final_kernel, stride=1,
+                                    padding=final_kernel // 2, groups=groups, bias=True))
+            setattr(self, head, nn.Sequential(*layers))
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv1d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0.0)
+        for head in self.heads:
+            if head == "cls_logits":
+                getattr(self, head)[-1].bias.data.fill_(self.init_bias)
+
+    def forward(self, x):
+        N, B, Q, C = x.shape
+        x = x.permute(1, 0, 3, 2).reshape(B, N * C, Q)  # "n b q c -> b (n c) q"
+        ret = {}
+        for head in self.heads:
+            y = getattr(self, head)(x)
+            ret[head] = y.view(B, N, -1, Q).permute(1, 0, 3, 2)  # "b (n c) q -> n b q c"
+        return ret
+
+
+class _ConvModule(nn.Module):
+    """mmcv ConvModule(conv_cfg=Conv2d, norm_cfg=BN2d): conv (no bias) -> bn -> relu; keys conv.*, bn.*."""
+
+    def __init__(self, cin, cout, k, padding):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+        self.activate = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.activate(self.bn(self.conv(x)))
+
+
+def _compute_dtype(precision):
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+class _CmtHeadBase(nn.Module):
+    """Everything the six head classes share: construction (cmt_head.py:208-318), position encodings
+    (:417-473), per-node decoder pass (:481-499 == cmt_head_coop.py:341-360) and the output tail (:501-547)."""
+
+    _has_bev = True
+    _has_img = True
+
+    def __init__(self, in_channels, num_query=900, hidden_dim=128, depth_num=64, norm_bbox=True,
+                 downsample_scale=8, scalar=10, noise_scale=1.0, noise_trans=0.0, dn_weight=1.0, split=0.75,
+                 train_cfg=None, test_cfg=None,
+                 common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
+                 tasks=None, transformer=None, bbox_coder=None, loss_cls=None, loss_bbox=None, loss_heatmap=None,
+                 separate_head=dict(type="SeparateMlpHead", init_bias=-2.19, final_kernel=3), init_cfg=None,
+                 **kwargs):
+        assert init_cfg is None
+        super().__init__()
+        tasks = tasks or [dict(num_class=10, class_names=["car"] * 10)]
+        self.num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.hidden_dim = hidden_dim
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.num_query = num_query
+        self.in_channels = in_channels
+        self.depth_num = depth_num
+        self.norm_bbox = norm_bbox
+        self.downsample_scale = downsample_scale
+        self.scalar = scalar
+        self.bbox_noise_scale = noise_scale
+        self.bbox_noise_trans = noise_trans
+        self.dn_weight = dn_weight
+        self.split = split
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.pc_range = self.bbox_coder.pc_range
+        self.fp16_enabled = False
+        self.precision = "bf16"
+
+        self.shared_conv = _ConvModule(in_channels, hidden_dim, 3, 1) if self._has_bev else None
+        transformer = ConfigDict(copy.deepcopy(transformer))
+        self.transformer = TRANSFORMER.build(transformer)
+        self.reference_points = nn.Embedding(num_query, 3)
+        self.bev_embedding = nn.Sequential(nn.Linear(hidden_dim * 2, hidden_dim), nn.ReLU(inplace=True),
+                                           nn.Linear(hidden_dim, hidden_dim))
+        self.rv_embedding = nn.Sequential(nn.Linear(depth_num * 3, hidden_dim * 4), nn.ReLU(inplace=True),
+                                          nn.Linear(hidden_dim * 4, hidden_dim)) if self._has_img else None
+        self.task_heads = nn.ModuleList()
+        for num_cls in self.num_classes:
+            heads = copy.deepcopy(dict(common_heads))
+            heads.update(dict(cls_logits=(num_cls, 2)))
+            sh = dict(copy.deepcopy(separate_head))
+            sh.update(in_channels=hidden_dim, heads=heads, num_cls=num_cls, groups=transformer.decoder.num_layers)
+            self.task_heads.append(HEADS.build(sh))
+        self._cache = {}
+
+    # ------------------------------------------------------------------------------------
+    def init_weights(self):
+        self.transformer.init_weights()
+        for th in self.task_heads:
+            th.init_weights()
+        nn.init.uniform_(self.reference_points.weight.data, 0, 1)
+
+    def set_precision(self, precision):
+        """'bf16' (tcgen05 kernels, default) or 'fp32' (CUDA-core verification mode)."""
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.transformer.set_precision(precision)
+        self._cache.clear()
+        return self
+
+    @property
+    def coords_bev(self):
+        """cmt_head.py:324-337."""
+        cfg = self.train_cfg if self.train_cfg else self.test_cfg
+        x_size = cfg["grid_size"][1] // self.downsample_scale
+        y_size = cfg["grid_size"][0] // self.downsample_scale
+        by, bx = torch.meshgrid(torch.linspace(0, x_size - 1, x_size), torch.linspace(0, y_size - 1, y_size),
+                                indexing="ij")
+        bx = (bx + 0.5) / x_size
+        by = (by + 0.5) / y_size
+        return torch.cat([bx[None], by[None]], dim=0).view(2, -1).transpose(1, 0)
+
+    def prepare_for_dn(self, batch_size, reference_points, img_metas):
+        if self.training:
+            raise NotImplementedError("denoising queries are training-only (cmt_head.py:339-408)")
+        return reference_points.unsqueeze(0).repeat(batch_size, 1, 1), None, None
+
+    # -- MLPs on the tcgen05 GEMM ---------------------------------------------------------
+    def _mlp_weights(self, name):
+        seq = getattr(self, name)
+        dt = _compute_dtype(self.precision)
+        key = (name, dt, seq[0].weight._version, seq[0].weight.data_ptr(), seq[2].weight._version,
+               seq[2].weight.data_ptr(), seq[0].bias._version, seq[2].bias._version)
+        hit = self._cache.get("w_" + name)
+        if hit is None or hit[0] != key:
+            hit = (key, (seq[0].weight.detach().to(dt).contiguous(), seq[0].bias.detach().float().contiguous(),
+                         seq[2].weight.detach().to(dt).contiguous(), seq[2].bias.detach().float().contiguous()))
+            self._cache["w_" + name] = hit
+        return hit[1]
+
+    def _mlp(self, name, x):
+        """Linear -> ReLU -> Linear (cmt_head.py:292-301); hidden activation in the compute dtype, fp32 out."""
+        w0, b0, w1, b1 = self._mlp_weights(name)
+        dt = _compute_dtype(self.precision)
+        h = ops.linear(x.to(dt), w0, b0, relu=True, out_dtype=dt)
+        return ops.linear(h, w1, b1, out_dtype=torch.float32)
+
+    # -- position encodings -----------------------------------------------------------------
+    def _matrices(self, img_metas, device):
+        """Host float64 inverse -> fp32 -> device, as cmt_head.py:428-429,441-444. [B,V,4,4] each."""
+        l2i = np.stack([np.asarray(m["lidar2img"], dtype=np.float64) for m in img_metas])
+        i2l = np.linalg.inv(l2i)
+        both = torch.from_numpy(np.stack([l2i, i2l]).astype(np.float32)).to(device, non_blocking=True)
+        return both[0].contiguous(), both[1].contiguous()
+
+    def _rv_pe(self, img_feats, img_metas, mats=None):
+        """cmt_head.py:417-433 -> [B*V,H,W,C] fp32."""
+        BN, C, H, W = img_feats.shape
+        pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
+        if mats is None:
+            mats = self._matrices(img_metas, img_feats.device)
+        dt = _compute_dtype(self.precision)
+        coords = ops.ray_pe(mats[1].reshape(-1, 4, 4), H, W, self.depth_num, pad_h, pad_w, self.pc_range, out_dtype=dt)
+        return self._mlp("rv_embedding", coords)
+
+    def _bev_pos_embed(self, device):
+        """bev_embedding(pos2embed(coords_bev)) (cmt_head.py:489): input independent -> cached per weights."""
+        w = self._mlp_weights("bev_embedding")
+        key = (id(w[0]), str(device), self.precision)
+        hit = self._cache.get("bev_pos")
+        if hit is None or hit[0] != key:
+            dt = _compute_dtype(self.precision)
+            emb = pos2embed(self.coords_bev.to(device), num_pos_feats=self.hidden_dim, out_dtype=dt)
+            hit = (key, self._mlp("bev_embedding", emb))
+            self._cache["bev_pos"] = hit
+        return hit[1]
+
+    def _bev_query_embed(self, ref_points, img_metas):
+        dt = _compute_dtype(self.precision)
+        return self._mlp("bev_embedding", pos2embed(ref_points, num_pos_feats=self.hidden_dim, out_dtype=dt))
+
+    def _rv_query_embed(self, ref_points, img_metas, mats=None):
+        """cmt_head.py:439-467."""
+        pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
+        if mats is None:
+            mats = self._matrices(img_metas, ref_points.device)
+        dt = _compute_dtype(self.precision)
+        feats, mask = ops.ray_query_pe(ref_points.contiguous(), mats[0], mats[1], self.depth_num, pad_h, pad_w,
+                                       self.pc_range, out_dtype=dt)
+        emb = self._mlp("rv_embedding", feats)
+        return ops.masked_view_sum(emb, mask)
+
+    def query_embed(self, ref_points, img_metas, mats=None):
+        ref_points = inverse_sigmoid(ref_points.clone()).sigmoid()
+        bev = self._bev_query_embed(ref_points, img_metas)
+        rv = self._rv_query_embed(ref_points, img_metas, mats) if self._has_img else None
+        return bev, rv
+
+    # -- one node: shared_conv -> PEs -> transformer -> nan_to_num ---------------------------
+    def get_outs_dec(self, x, x_img, img_metas, reference_points, attn_mask):
+        if self.training:
+            raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")
+        dev = (x if x is not None else x_img).device
+        if dev.type != "cuda":
+            raise RuntimeError("CmtHead needs CUDA tensors: libcmtcoop_b200 has no CPU fallback")
+        mats = self._matrices(img_metas, dev) if self._has_img else None
+        bev_q, rv_q = self.query_embed(reference_points, img_metas, mats)
+        query_embeds = bev_q if rv_q is None else bev_q + rv_q
+        if self._has_bev and self._has_img:
+            x = self.shared_conv(x)
+            rv_pos = self._rv_pe(x_img, img_metas, mats)
+            outs_dec, _ = self.transformer(x, x_img, query_embeds, self._bev_pos_embed(dev), rv_pos,
+                                           attn_masks=attn_mask)
+        elif self._has_bev:
+            x = self.shared_conv(x)
+            mask = None
+            outs_dec, _ = self.transformer(x, mask, query_embeds, self._bev_pos_embed(dev), attn_masks=attn_mask)
+        else:
+            rv_pos = self._rv_pe(x_img, img_metas, mats)
+            outs_dec, _ = self.transformer(x_img, query_embeds, rv_pos, attn_masks=attn_mask, bs=len(img_metas))
+        return torch.nan_to_num(outs_dec)
+
+    # -- task heads + reference-point decode (cmt_head.py:501-547, eval branch) ---------------
+    def _finish(self, outs_dec, reference_points):
+        reference = inverse_sigmoid(reference_points.clone())
+        pc = self.pc_range
+        ret_dicts = []
+        for task in self.task_heads:
+            outs = task(outs_dec)
+            center = (outs["center"] + reference[None, :, :, :2]).sigmoid()
+            height = (outs["height"] + reference[None, :, :, 2:3]).sigmoid()
+            _center, _height = center.new_zeros(center.shape), height.new_zeros(height.shape)
+            _center[..., 0:1] = center[..., 0:1] * (pc[3] - pc[0]) + pc[0]
+            _center[..., 1:2] = center[..., 1:2] * (pc[4] - pc[1]) + pc[1]
+            _height[..., 0:1] = height[..., 0:1] * (pc[5] - pc[2]) + pc[2]
+            outs["center"] = _center
+            outs["height"] = _height
+            ret_dicts.append(outs)
+        return ret_dicts
+
+    def get_bboxes(self, preds_dicts, img_metas, img=None, rescale=False):
+        """cmt_head.py:905-919."""
+        preds_dicts = self.bbox_coder.decode(preds_dicts)
+        ret_list = []
+        for i in range(len(preds_dicts)):
+            preds = preds_dicts[i]
+            bboxes = preds["bboxes"]
+            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+            box_type = img_metas[i].get("box_type_3d")
+            if box_type is not None:
+                bboxes = box_type(bboxes, bboxes.size(-1))
+            ret_list.append([bboxes, preds["scores"], preds["labels"]])
+        return ret_list
+
+
+@HEADS.register_module()
+class CmtHead(_CmtHeadBase):
+    """cmt_head.py:206-919 (multimodal: BEV + camera tokens)."""
+
+    def forward_single(self, x, x_img, img_metas):
+        reference_points = self.reference_points.weight
+        reference_points, attn_mask, mask_dict = self.prepare_for_dn(x.shape[0], reference_points, img_metas)
+        outs_dec = self.get_outs_dec(x, x_img, img_metas, reference_points, attn_mask)
+        return self._finish(outs_dec, reference_points)
+
+    def forward(self, pts_feats, img_feats=None, img_metas=None):
+        img_metas = [img_metas for _ in range(len(pts_feats))]
+        return multi_apply(self.forward_single, pts_feats, img_feats, img_metas)
+
+
+@HEADS.register_module()
+class CmtImageHead(CmtHead):
+    """cmt_head.py:922-999 (camera only; shared_conv is None)."""
+    _has_bev = False
+
+    def forward_single(self, x, x_img, img_metas):
+        assert x is None
+        reference_points = self.reference_points.weight
+        reference_points, attn_mask, mask_dict = self.prepare_for_dn(len(img_metas), reference_points, img_metas)
+        outs_dec = self.get_outs_dec(None, x_img, img_metas, reference_points, attn_mask)
+        return self._finish(outs_dec, reference_points)
+
+
+@HEADS.register_module()
+class CmtLidarHead(CmtHead):
+    """cmt_head.py:1002-1085 (LiDAR only; rv_embedding is None)."""
+    _has_img = False
+
+    def forward_single(self, x, x_img, img_metas):
+        assert x_img is None
+        reference_points = self.reference_points.weight
+        reference_points, attn_mask, mask_dict = self.prepare_for_dn(x.shape[0], reference_points, img_metas)
+        outs_dec = self.get_outs_dec(x, None, img_metas, reference_points, attn_mask)
+        return self._finish(outs_dec, reference_points)

@@ -1,0 +1,133 @@
+"""CmtTransformer / CmtLidarTransformer / CmtImageTransformer with the reference's signatures
+(projects/mmdet3d_plugin/models/utils/cmt_transformer.py:48-282).
+
+Where the reference materialises `memory` and `pos_embed` as two [N_kv,B,C] fp32 tensors
+(rearrange + cat + repeat, :105-110) and lets every decoder layer redo `key + key_pos` and the K/V
+projections, these classes run ONE fused gather kernel (NCHW -> token-major, BEV ++ image concat,
++pos, cast) and ONE pair of all-layer K / V^T projection GEMMs, then hand the decoder a KVCache.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .attention import KVCache
+from .petr_transformer import PETRMultiheadFlashAttention, build_transformer_layer_sequence
+from .registry import TRANSFORMER
+
+
+def _compute_dtype(precision):
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+class _CmtTransformerBase(nn.Module):
+    def __init__(self, encoder=None, decoder=None, init_cfg=None, cross=False):
+        super().__init__()
+        self.encoder = build_transformer_layer_sequence(encoder) if encoder is not None else None
+        self.decoder = build_transformer_layer_sequence(decoder)
+        self.embed_dims = self.decoder.embed_dims
+        self.cross = cross
+        self.precision = "bf16"
+        self._kv_w = None
+        self._is_init = False
+
+    def init_weights(self):
+        # follow the official DETR init (cmt_transformer.py:77-82): xavier-uniform on every >1-dim weight
+        for m in self.modules():
+            if hasattr(m, "weight") and isinstance(m.weight, torch.Tensor) and m.weight.dim() > 1:
+                nn.init.xavier_uniform_(m.weight)
+                if getattr(m, "bias", None) is not None:
+                    nn.init.constant_(m.bias, 0.0)
+        self._is_init = True
+
+    def set_precision(self, precision):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        for m in self.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+
+    # -- hoisted all-layer K / V projection ---------------------------------------------------
+    def _cross_attns(self):
+        out = []
+        for layer in self.decoder.layers:
+            ca = [a for a, op in zip(layer.attentions, [o for o in layer.operation_order if o.endswith("attn")])
+                  if op == "cross_attn"]
+            assert len(ca) == 1 and isinstance(ca[0], PETRMultiheadFlashAttention), \
+                "cross-attention must be PETRMultiheadFlashAttention (as in every reference config)"
+            out.append(ca[0].attn)
+        return out
+
+    def _stacked_kv_weights(self):
+        mhas = self._cross_attns()
+        dt = _compute_dtype(self.precision)
+        key = (dt,) + tuple((m.in_proj_weight._version, m.in_proj_weight.data_ptr(),
+                             None if m.in_proj_bias is None else m.in_proj_bias._version) for m in mhas)
+        if self._kv_w is None or self._kv_w[0] != key:
+            E = self.embed_dims
+            wk = torch.cat([m.in_proj_weight.detach()[E:2 * E] for m in mhas]).to(dt).contiguous()
+            wv = torch.cat([m.in_proj_weight.detach()[2 * E:] for m in mhas]).to(dt).contiguous()
+            if mhas[0].in_proj_bias is not None:
+                bk = torch.cat([m.in_proj_bias.detach()[E:2 * E] for m in mhas]).float().contiguous()
+                bv = torch.cat([m.in_proj_bias.detach()[2 * E:] for m in mhas]).float().contiguous()
+            else:
+                bk = bv = None
+            self._kv_w = (key, (wk, bk, wv, bv))
+        return self._kv_w[1]
+
+    def build_kv_cache(self, x_bev, x_img, bev_pos, rv_pos, B, V):
+        """gather (K4) + all-layer K / V^T projection (K2).  Returns (KVCache, xv [B,N_kv,C])."""
+        dt = _compute_dtype(self.precision)
+        xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt)
+        wk, bk, wv, bv = self._stacked_kv_weights()
+        L = len(self.decoder.layers)
+        H = self.decoder.layers[0].attentions[-1].num_heads
+        k = ops.project_keys(xk, wk, bk, L, H)
+        vt = ops.project_values_t(xv, wv, bv, L, H)
+        return KVCache(k, vt, xk.shape[1]), xv
+
+    def _decode(self, cache, query_embed, attn_masks, reg_branch):
+        if self.training:
+            raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")
+        query_embed = query_embed.transpose(0, 1)  # [B,Nq,C] -> [Nq,B,C]
+        target = torch.zeros_like(query_embed)
+        out_dec = self.decoder(query=target, key=None, value=None, key_pos=None, query_pos=query_embed,
+                               key_padding_mask=None, attn_masks=[attn_masks, None], kv_cache=cache)
+        return out_dec.transpose(1, 2)  # [L,B,Nq,C]
+
+
+@TRANSFORMER.register_module()
+class CmtTransformer(_CmtTransformerBase):
+    """cmt_transformer.py:48-127: BEV + image tokens."""
+
+    def forward(self, x, x_img, query_embed, bev_pos_embed, rv_pos_embed, attn_masks=None, reg_branch=None):
+        bs = x.shape[0]
+        V = x_img.shape[0] // bs
+        cache, xv = self.build_kv_cache(x.contiguous(), x_img.contiguous(), bev_pos_embed.contiguous(),
+                                        rv_pos_embed.contiguous(), bs, V)
+        out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
+        return out_dec, xv.transpose(0, 1)  # memory as [N_kv,B,C] (compute dtype)
+
+
+@TRANSFORMER.register_module()
+class CmtLidarTransformer(_CmtTransformerBase):
+    """cmt_transformer.py:130-204: BEV tokens only. `mask` is accepted and ignored like the reference's
+    all-zero key_padding_mask."""
+
+    def forward(self, x, mask, query_embed, pos_embed, attn_masks=None, reg_branch=None):
+        bs = x.shape[0]
+        cache, xv = self.build_kv_cache(x.contiguous(), None, pos_embed.contiguous(), None, bs, 0)
+        out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
+        return out_dec, xv.transpose(0, 1)
+
+
+@TRANSFORMER.register_module()
+class CmtImageTransformer(_CmtTransformerBase):
+    """cmt_transformer.py:207-282: image tokens only."""
+
+    def forward(self, x_img, query_embed, rv_pos_embed, attn_masks=None, reg_branch=None, bs=2):
+        V = x_img.shape[0] // bs
+        cache, xv = self.build_kv_cache(None, x_img.contiguous(), None, rv_pos_embed.contiguous(), bs, V)
+        out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
+        return out_dec, xv.transpose(0, 1)

@@ -1,0 +1,134 @@
+/* libcmtcoop_b200 -- C ABI of the B200-native CMT / CMTCoop token-fusion hot path.
+ *
+ * Every entry point replaces one piece of the reference's Python/PyTorch path
+ * (suren3141/CMT-Cooperative-Perception, paths below are relative to
+ * projects/mmdet3d_plugin/).  Conventions:
+ *   - the caller (PyTorch) owns every buffer, workspace included; the library never
+ *     allocates, frees or synchronises device memory;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, negative = error (cmt_last_error_string() explains);
+ *     no exception crosses this boundary;
+ *   - sm_100a only: on any other device every launch entry returns CMT_ERR_ARCH.
+ *     There is no CPU or generic-CUDA fallback.
+ *   - dtype codes: CMT_F32 / CMT_BF16.
+ */
+#ifndef CMTCOOP_B200_H_
+#define CMTCOOP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMT_OK 0
+#define CMT_ERR_BAD_ARG (-1)
+#define CMT_ERR_CUDA (-2)
+#define CMT_ERR_ARCH (-3)
+#define CMT_ERR_WORKSPACE (-4)
+
+#define CMT_F32 0
+#define CMT_BF16 1
+#define CMT_BF16_SIMT 3 /* cmt_cross_attn_fwd only: bf16 operands through the fp32 CUDA-core kernel (comparator) */
+
+/* flags of cmt_gemm_bias_act */
+#define CMT_GEMM_RELU 1          /* out = max(out, 0)                                  */
+#define CMT_GEMM_BIAS_PER_ROW 2  /* bias indexed by output row (default: by column)    */
+#define CMT_GEMM_FORCE_SIMT 4    /* fp32 CUDA-core kernel even for bf16 operands       */
+
+int cmt_version(void);
+const char* cmt_last_error_string(void);
+/* 0 when device `dev` is sm_100 (B200), CMT_ERR_ARCH otherwise. */
+int cmt_check_device(int dev);
+
+/* ---- K1: camera-ray 3D position-encoding lift --------------------------------------
+ * Replaces the eager meshgrid/einsum/normalise block of CmtHead._rv_pe
+ * (models/dense_heads/cmt_head.py:417-432, same code cmt_head_coop.py:283-298).
+ * img2lidar: [n_cam,4,4] fp32 row-major = float32(inv_float64(lidar2img)) (cmt_head.py:428-429).
+ * out:       [n_cam,H,W,D*3] (feature index 3*k+c, cmt_head.py:433), fp32 or bf16.
+ * pc_range:  6 host floats.  Token index inside a frame is cam*H*W + i*W + j. */
+int cmt_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, int D, float pad_h,
+               float pad_w, const float* pc_range_host, int out_dtype, void* stream);
+
+/* ---- K1b: reference-point re-projection for the query embedding ---------------------
+ * Replaces CmtHead._rv_query_embed up to the rv_embedding MLP (cmt_head.py:439-464).
+ * ref:       [B,Nq,3] fp32 in [0,1] (already inverse_sigmoid(...).sigmoid()'ed, :470)
+ * lidar2img: [B,V,4,4] fp32, img2lidar: [B,V,4,4] fp32
+ * out:       [B,V,Nq,D*3] (fp32|bf16), mask: [B,V,Nq] fp32 (1.0 inside image & z>0). */
+int cmt_ray_query_pe(const float* ref, const float* lidar2img, const float* img2lidar, void* out,
+                     float* mask, int B, int V, int Nq, int D, float pad_h, float pad_w,
+                     const float* pc_range_host, int out_dtype, void* stream);
+
+/* out[b,n,:] = sum_v mask[b,v,n] * emb[b,v,n,:]  (cmt_head.py:466). emb fp32|bf16, out fp32. */
+int cmt_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq,
+                        int C, int emb_dtype, void* stream);
+
+/* ---- sine/cosine BEV embedding ------------------------------------------------------
+ * pos2embed (cmt_head.py:40-50) including its `dim_t = 2*(i//2)/F + 1` divisor.
+ * pos: [N,pos_stride] fp32 (only columns 0 (x) and 1 (y) are read); out: [N,2F] = cat(emb(y), emb(x)). */
+int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype,
+                  void* stream);
+
+/* ---- K4: token gather / transpose / concat / pos-add / cast -------------------------
+ * Replaces the rearrange + cat + repeat of CmtTransformer.forward
+ * (models/utils/cmt_transformer.py:105-110) fused with `key = key + key_pos`
+ * (models/utils/petr_transformer.py:296-299).
+ * x_bev:   [B,C,n_bev] fp32 NCHW-flattened or NULL (n_bev = 0)
+ * x_img:   [B*V,C,n_img] fp32 or NULL (V = 0)
+ * bev_pos: [n_bev,C] fp32 (batch-invariant), rv_pos: [B*V*n_img,C] fp32
+ * xk = mem + pos, xv = mem, both [B,N_kv,C] token-major, N_kv = n_bev + V*n_img,
+ * order BEV tokens then image tokens view-major. out dtype fp32|bf16. */
+int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+                      const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
+                      int n_img, int out_dtype, void* stream);
+
+/* ---- K2: projection / MLP GEMM ------------------------------------------------------
+ * C = act((A * B^T + bias) * alpha); A:[M,K] (lda), B:[N,K] (ldb), both row-major, K contiguous.
+ * Replaces F.linear in _in_projection_packed / out_proj (models/utils/attention.py:21-27,138)
+ * and the nn.Linear+ReLU pairs of rv_embedding / bev_embedding (cmt_head.py:292-301).
+ * Batched: `batch` problems, element strides strideA/strideB (0 = shared operand)/strideC.
+ * Output addressing ("column blocks"): element (m,n) of batch z is stored at
+ *     C + z*strideC + (n / cb)*cb_stride + m*ldc + (n % cb)
+ * cb >= N gives a plain row-major matrix; cb = 32 with ldc = 32 gives the per-head
+ * [.., H, tokens, 32] layout the attention kernel reads.
+ * in_dtype bf16 -> TMA + tcgen05 kernel (fp32 accumulate in TMEM); in_dtype fp32 -> fp32
+ * CUDA-core kernel (verification mode).  Requirements for bf16: K % 8 == 0, lda/ldb % 8 == 0,
+ * 16-byte aligned bases, and (cb >= N or cb % 32 == 0). */
+int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N,
+                      int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t cb, int64_t cb_stride,
+                      int batch, int64_t strideA, int64_t strideB, int64_t strideC, float alpha,
+                      int flags, int in_dtype, int out_dtype, void* stream);
+
+/* ---- K3: flash cross-attention ------------------------------------------------------
+ * Replaces flash_attn_unpadded_kvpacked_func as called by FlashAttention.forward
+ * (models/utils/attention.py:46-92; softmax(Q K^T / sqrt(d)) V, non-causal, no dropout).
+ * q:   [B,Nq,H*32] row-major (row stride q_ld), ALREADY multiplied by log2(e)/sqrt(32)
+ * k:   per (b,h) a [N_kv,32] matrix (row stride 32) at k + b*k_bstride + h*k_hstride
+ * vt:  per (b,h) a [32,N_kv] matrix (row stride v_ld) at vt + b*v_bstride + h*v_hstride
+ * Only tokens [kv_begin,kv_end) are attended (multi-GPU / split-KV partials).
+ * o:   [B,Nq,H*32] (o_dtype, row stride H*32), normalised over the attended tokens
+ * lse: [B,H,Nq] fp32 natural-log sum-exp of the scaled scores over the attended tokens, or NULL
+ * dtype bf16 -> tcgen05 kernel, work split over all SMs along the KV axis with partials in
+ * `workspace` (cmt_cross_attn_workspace_bytes) merged by a second kernel; dtype fp32 -> fp32
+ * CUDA-core kernel.  Head dim is fixed at 32 (256/8, the only value the reference configs use). */
+size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens);
+int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B,
+                       int H, int Nq, int N_kv, int kv_begin, int kv_end, int64_t q_ld,
+                       int64_t k_bstride, int64_t k_hstride, int64_t v_bstride, int64_t v_hstride,
+                       int64_t v_ld, int dtype, int o_dtype, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Log-sum-exp merge of G partial attention results (KV-token split across GPUs or streams):
+ * o_parts [G,B,Nq,H*32] fp32, lse_parts [G,B,H,Nq] fp32 (natural log) -> o [B,Nq,H*32], lse. */
+int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B,
+                  int H, int Nq, int o_dtype, void* stream);
+
+/* ---- cooperative V2I merge ----------------------------------------------------------
+ * out = max(nan_to_num(a), nan_to_num(b)) element-wise (cmt_head_coop.py:358,383-389). */
+int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMTCOOP_B200_H_ */
