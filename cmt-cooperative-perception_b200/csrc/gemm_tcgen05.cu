@@ -7,7 +7,7 @@
 //   warp 1      MMA issuer    : one elected thread, tcgen05.mma cta_group::1 kind::f16,
 //                               M=128 x N=256 x K=16 per instruction, accumulator in TMEM
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, ping-pong)
-//   warps 4..7  epilogue      : tcgen05.ld 32x32b -> bias / alpha / ReLU -> bf16|fp32 -> global,
+//   warps 4..11 epilogue      : tcgen05.ld 32x32b -> bias / alpha / ReLU -> bf16|fp32 -> global,
 //                               overlapped with the next tile's main loop
 //
 // Replaces F.linear in models/utils/attention.py:21-27,138 and the PE MLPs of
@@ -23,7 +23,7 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;  // 4 control warps + 8 epilogue warps
 }  // namespace gemm
 
 struct TcGemmParams {
@@ -63,7 +63,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -127,39 +127,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ------------------------------- epilogue -------------------------------
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        // 8 warps: warp w reads TMEM lane quadrant (w & 3) and column half ((w - 4) >> 2), so every
+        // scheduler has two epilogue warps to overlap TMEM / global latencies.  All option tests
+        // (bias kind, alpha, relu, dtype) are hoisted out of the per-element loops.
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const bool has_bias = p.bias != nullptr;
+        const bool col_bias = has_bias && !p.bias_per_row;
+        const bool scale = p.alpha != 1.0f;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int z = tile / tiles_per_batch;
             const int r = tile - z * tiles_per_batch;
             const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const int m = mt * BM + quad * 32 + lane;
             const bool m_ok = m < p.M;
-            const float row_bias = (p.bias && p.bias_per_row && m_ok) ? __ldg(p.bias + m) : 0.0f;
+            const float row_bias = (has_bias && p.bias_per_row && m_ok) ? __ldg(p.bias + m) : 0.0f;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 const int n0 = nt * BN + c * 32;
                 if (n0 >= p.N) break;  // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(t_row + c * 32, v);
-                tc_wait_ld();
-                if (m_ok) {
-                    float f[32];
+                const bool full = (n0 + 32 <= p.N);
+                float f[32];
+                if (col_bias) {
+                    if (full) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);  // n0 % 32 == 0
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(v[i]);
-                        if (p.bias) x += p.bias_per_row ? row_bias : ((n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f);
-                        x *= p.alpha;
-                        if (p.relu) x = fmaxf(x, 0.0f);
-                        f[i] = x;
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = __ldg(b4 + i);
+                            f[4 * i] = b.x; f[4 * i + 1] = b.y; f[4 * i + 2] = b.z; f[4 * i + 3] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = row_bias;
+                }
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
+                if (scale) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] *= p.alpha;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+                }
+                if (m_ok) {
                     const long long off = z * p.strideC + (n0 / p.cb) * p.cb_stride +
                                           static_cast<long long>(m) * p.ldc + (n0 % p.cb);
-                    const bool full = (n0 + 32 <= p.N);
                     if (p.out_bf16) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
                         if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -173,7 +198,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 reinterpret_cast<uint4*>(dst)[i] = w;
                             }
                         } else {
-#pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (n0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
                         }
@@ -185,7 +209,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 reinterpret_cast<float4*>(dst)[i] =
                                     make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
                         } else {
-#pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (n0 + i < p.N) dst[i] = f[i];
                         }

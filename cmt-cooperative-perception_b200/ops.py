@@ -28,6 +28,20 @@ def _count(n=1):
     _launches += n
 
 
+_profile = {}  # op name -> list of (start, end) CUDA events recorded on the launching stream
+
+
+def profile_events(name: str, enable: bool):
+    """bench.py hook: time every launch of op `name` with CUDA events on the stream it is launched on.
+    Enabling starts a fresh list; disabling synchronises and returns the per-launch durations in ms."""
+    if enable:
+        _profile[name] = []
+        return None
+    pairs = _profile.pop(name, [])
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
 def _dt(dtype) -> int:
     if dtype == torch.float32:
         return CMT_F32
@@ -108,7 +122,7 @@ def masked_view_sum(emb, mask):
 
 def pos2embed(pos, num_pos_feats=128, out_dtype=torch.bfloat16):
     """pos2embed (cmt_head.py:40-50). pos [...,>=2] fp32 -> [..., 2*num_pos_feats]."""
-    pos = _cuda(pos, "pos", torch.float32)
+    pos = _cuda(pos.contiguous(), "pos", torch.float32)
     lead = pos.shape[:-1]
     stride = pos.shape[-1]
     N = int(math.prod(lead))
@@ -253,10 +267,17 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         with torch.cuda.device(q.device):
             ws_bytes = int(lib.cmt_cross_attn_workspace_bytes(B, H, Nq, kv_end - kv_begin))
         ws = _workspace(q.device, ws_bytes)
+    ev = _profile.get("cross_attn")
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     with torch.cuda.device(q.device):
         rc = lib.cmt_cross_attn_fwd(_ptr(q), kp, vp, _ptr(o), _ptr(lse), B, H, Nq, N_kv, kv_begin, kv_end, HD,
                                     L * H * N_kv * HEAD_DIM, N_kv * HEAD_DIM, L * H * HEAD_DIM * ld, HEAD_DIM * ld,
                                     ld, dt, _dt(o_dtype), _ptr(ws), ws_bytes, _stream(q))
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
     _lib.check(rc, "cmt_cross_attn_fwd")
     _count(2 if dt == CMT_BF16 else 1)
     return (o, lse) if return_lse else o

@@ -120,6 +120,25 @@ def _compute_dtype(precision):
     return torch.float32 if precision == "fp32" else torch.bfloat16
 
 
+class _torch_math:
+    """fp32 verification mode must be fp32 end to end: the torch ops that stay on the path (cuDNN
+    shared_conv / Conv1d task heads, cuBLAS self-attention and FFN) default to TF32 on this GPU."""
+
+    def __init__(self, precision):
+        self.strict = precision == "fp32"
+
+    def __enter__(self):
+        if self.strict:
+            self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        if self.strict:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
 class _CmtHeadBase(nn.Module):
     """Everything the six head classes share: construction (cmt_head.py:208-318), position encodings
     (:417-473), per-node decoder pass (:481-499 == cmt_head_coop.py:341-360) and the output tail (:501-547)."""
@@ -156,6 +175,8 @@ class _CmtHeadBase(nn.Module):
         self.pc_range = self.bbox_coder.pc_range
         self.fp16_enabled = False
         self.precision = "bf16"
+        # bench.py times "CmtTransformer+PE" from the post-shared_conv BEV map; set False then
+        self.apply_shared_conv = True
 
         self.shared_conv = _ConvModule(in_channels, hidden_dim, 3, 1) if self._has_bev else None
         transformer = ConfigDict(copy.deepcopy(transformer))
@@ -279,6 +300,10 @@ class _CmtHeadBase(nn.Module):
 
     # -- one node: shared_conv -> PEs -> transformer -> nan_to_num ---------------------------
     def get_outs_dec(self, x, x_img, img_metas, reference_points, attn_mask):
+        with _torch_math(self.precision):
+            return self._get_outs_dec(x, x_img, img_metas, reference_points, attn_mask)
+
+    def _get_outs_dec(self, x, x_img, img_metas, reference_points, attn_mask):
         if self.training:
             raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")
         dev = (x if x is not None else x_img).device
@@ -288,12 +313,12 @@ class _CmtHeadBase(nn.Module):
         bev_q, rv_q = self.query_embed(reference_points, img_metas, mats)
         query_embeds = bev_q if rv_q is None else bev_q + rv_q
         if self._has_bev and self._has_img:
-            x = self.shared_conv(x)
+            x = self.shared_conv(x) if self.apply_shared_conv else x
             rv_pos = self._rv_pe(x_img, img_metas, mats)
             outs_dec, _ = self.transformer(x, x_img, query_embeds, self._bev_pos_embed(dev), rv_pos,
                                            attn_masks=attn_mask)
         elif self._has_bev:
-            x = self.shared_conv(x)
+            x = self.shared_conv(x) if self.apply_shared_conv else x
             mask = None
             outs_dec, _ = self.transformer(x, mask, query_embeds, self._bev_pos_embed(dev), attn_masks=attn_mask)
         else:
@@ -303,6 +328,11 @@ class _CmtHeadBase(nn.Module):
 
     # -- task heads + reference-point decode (cmt_head.py:501-547, eval branch) ---------------
     def _finish(self, outs_dec, reference_points):
+        # the task heads feed the top-k: always strict fp32 (no TF32), they cost ~0.1 GF
+        with _torch_math("fp32"):
+            return self._finish_impl(outs_dec, reference_points)
+
+    def _finish_impl(self, outs_dec, reference_points):
         reference = inverse_sigmoid(reference_points.clone())
         pc = self.pc_range
         ret_dicts = []

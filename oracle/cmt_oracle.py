@@ -298,7 +298,8 @@ def node_outs_dec(sd, cfg, x, x_img, metas, stages=None):
     ref = sd["reference_points.weight"].unsqueeze(0).repeat(B, 1, 1)      # cmt_head.py:410-411 (eval)
     bev_pos = rv_pos = None
     if x is not None:
-        x = _shared_conv(x, sd)
+        if cfg.get("_apply_shared_conv", True):  # bench scope: "CmtTransformer+PE" starts after shared_conv
+            x = _shared_conv(x, sd)
         grid = cfg["test_cfg"]["grid_size"]
         bev_pos = mlp2(pos2embed(coords_bev(grid, cfg.get("downsample_scale", 8)), hidden), sd, "bev_embedding")
     r = inverse_sigmoid(ref.clone()).sigmoid()                             # cmt_head.py:470

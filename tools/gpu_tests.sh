@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 run() {
   name=$1; shift
   echo "=== $name"
-  timeout 900 python -m pytest -m gpu -q -x --no-header -p no:cacheprovider "$@" > gpurun_out/test_$name.log 2>&1
+  timeout 900 python -m pytest -m gpu -q --no-header -p no:cacheprovider "$@" > gpurun_out/test_$name.log 2>&1
   echo "exit=$? $(tail -n 3 gpurun_out/test_$name.log | tr '\n' ' ')"
 }
 run simple tests/test_gpu_kernels.py -k "not gemm and not attention"

@@ -1,0 +1,63 @@
+"""Launch each hot kernel a few times at the nuScenes-multimodal shape (B=8) for an ncu capture.
+usage: python tools/prof_kernels.py [kproj|vproj|mlp1|mlp2|attn|gather|raype|all]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cmtcoop_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = "cuda:0"
+B, N_kv, C, L, H, Nq = 8, 56400, 256, 6, 8, 900
+torch.manual_seed(0)
+
+
+def timed(name, fn):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per launch", flush=True)
+
+
+if which in ("kproj", "vproj", "attn", "all"):
+    x = torch.randn(B, N_kv, C, device=dev).bfloat16()
+    w = (torch.randn(L * H * 32, C, device=dev) / 16).bfloat16()
+    b = torch.randn(L * H * 32, device=dev)
+    k = torch.empty((B, L, H, N_kv, 32), dtype=torch.bfloat16, device=dev)
+    vt = torch.empty((B, L, H, 32, N_kv), dtype=torch.bfloat16, device=dev)
+    if which in ("kproj", "all", "attn"):
+        timed("kproj", lambda: ops.project_keys(x, w, b, L, H, out=k))
+    if which in ("vproj", "all", "attn"):
+        timed("vproj", lambda: ops.project_values_t(x, w, b, L, H, out=vt))
+    if which in ("attn", "all"):
+        q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
+        timed("attn", lambda: ops.cross_attn(q, k, vt, 2))
+if which in ("mlp1", "mlp2", "all"):
+    M = 8 * 6 * 4000
+    a = torch.randn(M, 192, device=dev).bfloat16()
+    w0 = (torch.randn(1024, 192, device=dev) / 14).bfloat16()
+    b0 = torch.randn(1024, device=dev)
+    w1 = (torch.randn(256, 1024, device=dev) / 32).bfloat16()
+    b1 = torch.randn(256, device=dev)
+    h = ops.linear(a, w0, b0, relu=True)
+    if which in ("mlp1", "all"):
+        timed("mlp1", lambda: ops.linear(a, w0, b0, relu=True))
+    if which in ("mlp2", "all"):
+        timed("mlp2", lambda: ops.linear(h, w1, b1, out_dtype=torch.float32))
+if which in ("gather", "all"):
+    xb = torch.randn(B, 256, 180, 180, device=dev)
+    xi = torch.randn(B * 6, 256, 40, 100, device=dev)
+    bp = torch.randn(32400, 256, device=dev)
+    rp = torch.randn(B * 6 * 4000, 256, device=dev)
+    timed("gather", lambda: ops.gather_tokens(xb, xi, bp, rp, B, 6))
+if which in ("raype", "all"):
+    m = torch.eye(4, device=dev).repeat(B * 6, 1, 1).contiguous()
+    timed("raype", lambda: ops.ray_pe(m, 40, 100, 64, 640.0, 1600.0, [-54, -54, -5, 54, 54, 3]))
