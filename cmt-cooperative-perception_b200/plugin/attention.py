@@ -30,10 +30,11 @@ class KVCache:
     k:  [B, L, H, N_kv, 32]      vt: [B, L, H, 32, ld]
     """
 
-    def __init__(self, k, vt, n_kv):
+    def __init__(self, k, vt, n_kv, group=None):
         self.k = k
         self.vt = vt
-        self.n_kv = n_kv
+        self.n_kv = n_kv      # tokens held by THIS rank (all of them unless KV-split)
+        self.group = group    # torch.distributed group when the token axis is split across ranks
 
 
 class FlashAttention(nn.Module):
@@ -151,5 +152,22 @@ class FlashMHA(nn.Module):
             kk = ops.project_keys(k.to(dt).contiguous(), ws["wk"], ws["bk"], 1, self.num_heads)
             vt = ops.project_values_t(v.to(dt).contiguous(), ws["wv"], ws["bv"], 1, self.num_heads)
             kv_cache, layer_index = KVCache(kk, vt, k.shape[1]), 0
-        ctx = self.attend(q, kv_cache, layer_index)
+        if kv_cache.group is None:
+            ctx = self.attend(q, kv_cache, layer_index)
+        else:
+            ctx = self._attend_kv_split(q, kv_cache, layer_index)
         return self.project_out(ctx), None
+
+    def _attend_kv_split(self, q, cache: KVCache, layer: int):
+        """KV tokens are split across the ranks of `cache.group`: local partial (normalised O + LSE) ->
+        all-gather over NVLink (NCCL) -> log-sum-exp merge.  Queries are replicated."""
+        from .. import parallel
+        B, Nq, E = q.shape
+        if cache.n_kv > 0:
+            o_part, lse = self.attend(q, cache, layer, return_lse=True, o_dtype=torch.float32)
+        else:  # this rank holds no tokens: neutral element of the merge
+            o_part = torch.zeros((B, Nq, E), dtype=torch.float32, device=q.device)
+            lse = torch.full((B, self.num_heads, Nq), float("-inf"), dtype=torch.float32, device=q.device)
+        o_all, l_all = parallel.gather_partials(o_part, lse, cache.group)
+        ctx, _ = ops.lse_merge(o_all, l_all, o_dtype=_compute_dtype(self.precision))
+        return ctx

@@ -29,6 +29,7 @@ class _CmtTransformerBase(nn.Module):
         self.embed_dims = self.decoder.embed_dims
         self.cross = cross
         self.precision = "bf16"
+        self.kv_split_group = None
         self._kv_w = None
         self._is_init = False
 
@@ -83,9 +84,30 @@ class _CmtTransformerBase(nn.Module):
         wk, bk, wv, bv = self._stacked_kv_weights()
         L = len(self.decoder.layers)
         H = self.decoder.layers[0].attentions[-1].num_heads
+        group = self.kv_split_group
+        if group is not None:
+            # KV-token split: this rank projects and attends only its tile-aligned token range
+            import torch.distributed as dist
+            from .. import parallel
+            lo, hi = parallel.kv_split_range(xk.shape[1], dist.get_rank(group), dist.get_world_size(group))
+            if hi <= lo:
+                return KVCache(None, None, 0, group), xv
+            xk_l, xv_l = xk[:, lo:hi].contiguous(), xv[:, lo:hi].contiguous()
+            return KVCache(ops.project_keys(xk_l, wk, bk, L, H), ops.project_values_t(xv_l, wv, bv, L, H),
+                           hi - lo, group), xv
         k = ops.project_keys(xk, wk, bk, L, H)
         vt = ops.project_values_t(xv, wv, bv, L, H)
         return KVCache(k, vt, xk.shape[1]), xv
+
+    def enable_kv_split(self, group=None):
+        """Split the K/V token axis across the ranks of `group` (default: the WORLD group); every rank
+        must call forward with the SAME frames.  Pass `False` to switch back to frame sharding."""
+        if group is False:
+            self.kv_split_group = None
+            return self
+        import torch.distributed as dist
+        self.kv_split_group = group if group is not None else dist.group.WORLD
+        return self
 
     def _decode(self, cache, query_embed, attn_masks, reg_branch):
         if self.training:

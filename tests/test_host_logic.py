@@ -1,0 +1,118 @@
+"""Host-side mirror of the reference interface: registry / config building, state-dict keys, the
+torch-only stages (task heads, bbox coder) against the oracle on CPU, error behaviour, and the
+multi-GPU partition helpers.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from cmtcoop_b200 import _lib, ops, parallel, synth
+from cmtcoop_b200 import plugin
+from oracle import cmt_oracle as O
+
+
+@pytest.mark.parametrize("kind", synth.HEAD_KINDS)
+def test_reference_config_builds_and_keys_match_reference(kind, golden_dir):
+    cfg, _ = synth.mini_case(kind)
+    head = plugin.build_head(cfg)
+    assert type(head).__name__ == kind and not head.training
+    want = json.load(open(os.path.join(golden_dir, "state_dict_keys_mini.json")))[kind]
+    got = {k: list(v.shape) for k, v in head.state_dict().items()}
+    assert got == want  # names and shapes of the reference class, checkpoint-compatible
+
+
+def test_full_size_config_builds():
+    head = plugin.build_head(synth.head_cfg("CmtHead"))
+    assert head.num_query == 900 and len(head.transformer.decoder.layers) == 6
+    assert tuple(head.coords_bev.shape) == (180 * 180, 2)
+    ca = head.transformer.decoder.layers[0].attentions[1]
+    assert isinstance(ca, plugin.PETRMultiheadFlashAttention) and ca.attn.in_proj_bias is not None  # bias quirk
+
+
+def test_registry_names():
+    for reg, names in dict(HEADS=synth.HEAD_KINDS + ("SeparateTaskHead",),
+                           TRANSFORMER=("CmtTransformer", "CmtLidarTransformer", "CmtImageTransformer"),
+                           ATTENTION=("MultiheadAttention", "PETRMultiheadAttention", "PETRMultiheadFlashAttention"),
+                           TRANSFORMER_LAYER=("PETRTransformerDecoderLayer",),
+                           TRANSFORMER_LAYER_SEQUENCE=("PETRTransformerDecoder",),
+                           BBOX_CODERS=("MultiTaskBBoxCoder",)).items():
+        for n in names:
+            assert n in plugin.ALL[reg], (reg, n)
+    with pytest.raises(KeyError):
+        plugin.HEADS.get("NoSuchHead")
+
+
+def test_no_cpu_fallback_and_inference_only():
+    cfg, inputs = synth.mini_case("CmtLidarHead")
+    head = plugin.build_head(cfg)
+    x = torch.from_numpy(inputs["pts_feats"])
+    with pytest.raises((RuntimeError, _lib.CmtLibraryError)):
+        head.forward_single(x, None, inputs["img_metas"])          # CPU tensors are refused
+    with pytest.raises(_lib.CmtLibraryError):
+        ops.pos2embed(torch.rand(4, 2), 128)
+    head.train()
+    with pytest.raises(NotImplementedError):
+        head.prepare_for_dn(1, head.reference_points.weight, None)
+    mha = plugin.FlashMHA(256, 8, 0.1)
+    assert mha.bias == 0.1 and mha.in_proj_bias is not None            # attn_drop lands in `bias` (petr_transformer.py:226)
+    with pytest.raises(AssertionError):
+        plugin.FlashMHA(256, 4)                                         # head_dim 64: not on the reference path
+
+
+def test_task_heads_and_coder_match_oracle_cpu():
+    """The torch-only tail (SeparateTaskHead, reference-point decode, MultiTaskBBoxCoder) on CPU."""
+    for kind in ("CmtHead", "CmtLidarHead"):  # final_kernel 1 and 3
+        cfg, _ = synth.mini_case(kind)
+        head = plugin.build_head(cfg)
+        synth.load_synth_weights(head, 1)
+        g = torch.Generator().manual_seed(3)
+        outs_dec = torch.randn(2, 2, 96, 256, generator=g)
+        ref = head.reference_points.weight.detach().unsqueeze(0).repeat(2, 1, 1)
+        sd = {k: v.detach() for k, v in head.state_dict().items()}
+        want = O.decode_outputs(outs_dec, ref, sd, cfg)
+        with torch.no_grad():
+            got = head._finish(outs_dec, ref)
+        for name in want[0]:
+            assert torch.allclose(got[0][name], want[0][name], atol=1e-5, rtol=1e-5), (kind, name)
+        wb = O.bbox_decode(want, cfg)
+        gb = head.bbox_coder.decode([[got[0]]])
+        for i in range(2):
+            assert torch.equal(gb[i]["topk_index"], wb[i]["topk_index"])     # identical top-k query indices
+            assert torch.equal(gb[i]["labels"], wb[i]["labels"])
+
+
+def test_filter_img_metas():
+    meta = dict(vehicle_lidar2img=1, infrastructure_lidar2img=2, box_type_3d=3, vehicle_pad_shape=4)
+    v = plugin.get_vehicle_image_metas([meta])[0]
+    assert v == dict(lidar2img=1, pad_shape=4, box_type_3d=3, node="vehicle_")
+    i = plugin.get_infrastructure_image_metas([meta])[0]
+    assert i == dict(lidar2img=2, box_type_3d=3, node="infrastructure_")
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 100000), world=st.integers(1, 16))
+def test_kv_split_ranges_partition_the_tokens(n, world):
+    ranges = [parallel.kv_split_range(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
+        assert lo <= hi == lo2
+    assert all(lo % parallel.KV_TILE == 0 or lo == n for lo, _ in ranges)
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 1000), world=st.integers(1, 16))
+def test_frame_shards_partition_the_batch(n, world):
+    ranges = [parallel.shard_frames(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    sizes = [hi - lo for lo, hi in ranges]
+    assert max(sizes) - min(sizes) <= 1 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+def test_synth_is_deterministic():
+    a = synth.synth_tensor("transformer.decoder.layers.0.attentions.1.attn.in_proj_weight", (768, 256), 0)
+    b = synth.synth_tensor("transformer.decoder.layers.0.attentions.1.attn.in_proj_weight", (768, 256), 0)
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert abs(float(a[0, 0]) - float(a[0, 0])) == 0 and float(np.abs(a).max()) <= np.sqrt(6.0 / (256 + 768)) + 1e-7
