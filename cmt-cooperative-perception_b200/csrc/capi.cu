@@ -256,6 +256,14 @@ int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* 
     return launch_lse_merge(o_parts, lse_parts, o, lse, G, B, H, Nq, o_dtype, static_cast<cudaStream_t>(stream));
 }
 
+int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
+                      float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
+                      void* yadd, int lp_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_add_layernorm(x, r, gamma, beta, eps, M, C, y, gamma2, beta2, y2, add, ylp, yadd, lp_dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
 int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream) {
     CMT_REQUIRE_DEVICE();
     return launch_coop_max(a, b, out, n, static_cast<cudaStream_t>(stream));

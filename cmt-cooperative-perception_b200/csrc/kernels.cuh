@@ -44,6 +44,10 @@ int launch_gather_tokens(const float* x_bev, const float* x_img, const float* be
 int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
                      int B, int H, int Nq, int o_dtype, cudaStream_t stream);
+// norm_kernels.cu
+int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
+                         float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
+                         void* yadd, int lp_dtype, cudaStream_t stream);
 // simt_kernels.cu
 int launch_simt_gemm(const GemmArgs& g, int batch, int in_dtype, cudaStream_t stream);
 int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);

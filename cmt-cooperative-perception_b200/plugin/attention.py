@@ -161,10 +161,15 @@ class FlashMHA(nn.Module):
     def _attend_kv_split(self, q, cache: KVCache, layer: int):
         """KV tokens are split across the ranks of `cache.group`: local partial (normalised O + LSE) ->
         all-gather over NVLink (NCCL) -> log-sum-exp merge.  Queries are replicated."""
+        return self._merge_kv_split(self.project_q(q), cache, layer)
+
+    def _merge_kv_split(self, qp, cache: KVCache, layer: int):
+        """qp: already projected + pre-scaled queries [B,Nq,E]."""
         from .. import parallel
-        B, Nq, E = q.shape
+        B, Nq, E = qp.shape
+        q = qp
         if cache.n_kv > 0:
-            o_part, lse = self.attend(q, cache, layer, return_lse=True, o_dtype=torch.float32)
+            o_part, lse = ops.cross_attn(qp, cache.k, cache.vt, layer, return_lse=True, o_dtype=torch.float32)
         else:  # this rank holds no tokens: neutral element of the merge
             o_part = torch.zeros((B, Nq, E), dtype=torch.float32, device=q.device)
             lse = torch.full((B, self.num_heads, Nq), float("-inf"), dtype=torch.float32, device=q.device)

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import fused_decoder
 from .attention import KVCache
 from .petr_transformer import PETRMultiheadFlashAttention, build_transformer_layer_sequence
 from .registry import TRANSFORMER
@@ -30,6 +31,7 @@ class _CmtTransformerBase(nn.Module):
         self.cross = cross
         self.precision = "bf16"
         self.kv_split_group = None
+        self.use_fused_decoder = True  # False: module-by-module path (torch self-attention / LN / FFN)
         self._kv_w = None
         self._is_init = False
 
@@ -112,6 +114,8 @@ class _CmtTransformerBase(nn.Module):
     def _decode(self, cache, query_embed, attn_masks, reg_branch):
         if self.training:
             raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")
+        if self.use_fused_decoder and fused_decoder.supports(self.decoder, attn_masks, cache):
+            return fused_decoder.run(self.decoder, query_embed, cache, self.precision)  # [L,B,Nq,C]
         query_embed = query_embed.transpose(0, 1)  # [B,Nq,C] -> [Nq,B,C]
         target = torch.zeros_like(query_embed)
         out_dec = self.decoder(query=target, key=None, value=None, key_pos=None, query_pos=query_embed,

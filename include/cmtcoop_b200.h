@@ -124,6 +124,18 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B,
                   int H, int Nq, int o_dtype, void* stream);
 
+/* ---- decoder small ops: fused residual add + LayerNorm --------------------------------
+ * One launch for `query = norm(identity + attn_out)` of mmcv BaseTransformerLayer (post-norm order
+ * self_attn, norm, cross_attn, norm, ffn, norm) plus PETRTransformerDecoder's shared post_norm
+ * (models/utils/petr_transformer.py:363-371) and the casts / `query + query_pos` (:294-295) the
+ * next projection needs.  x, r (nullable), add (nullable): [M,C] fp32; C must be 256.
+ *   y    = LN(x + r; gamma, beta, eps)            fp32, required
+ *   y2   = LN(y; gamma2, beta2, eps)              fp32, optional (NULL)
+ *   ylp  = cast(y), yadd = cast(y + add)          lp_dtype (fp32|bf16), each optional (NULL) */
+int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps,
+                      int M, int C, float* y, const float* gamma2, const float* beta2, float* y2,
+                      const float* add, void* ylp, void* yadd, int lp_dtype, void* stream);
+
 /* ---- cooperative V2I merge ----------------------------------------------------------
  * out = max(nan_to_num(a), nan_to_num(b)) element-wise (cmt_head_coop.py:358,383-389). */
 int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream);
