@@ -250,6 +250,9 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
     return launch_simt_attn(a, dtype == CMT_BF16_SIMT ? CMT_BF16 : dtype, s);
 }
 
+// debug hook (not part of the public header): per-phase clock64 accounting of tc_attn_kernel, CTA 0
+int cmt_debug_attn_timing(void* dev_buf_32xi64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_32xi64)); }
+
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B, int H,
                   int Nq, int o_dtype, void* stream) {
     CMT_REQUIRE_DEVICE();

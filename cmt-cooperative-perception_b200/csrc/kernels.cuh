@@ -54,6 +54,7 @@ int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);
 // gemm_tcgen05.cu
 int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream);
 // attn_tcgen05.cu
+int tc_attn_set_timing_buffer(long long* dev_buf);
 size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens);
 int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 

@@ -209,7 +209,9 @@ def test_cross_attention(B, Nq, N_kv, lo, hi, mode):
         # P is rounded to bf16 before the PV product and exp2 is the MUFU approximation:
         # 2^-9 per element, averaged over many tokens
         assert _rel(o, want_o) < 4e-3, _rel(o, want_o)
-        assert (lse.cpu() - want_lse).abs().max() < 2e-3
+        # the row sum is accumulated on the tensor pipe from the bf16-rounded P (ones column): a row
+        # dominated by one key carries that key's 2^-9 rounding straight into LSE
+        assert (lse.cpu() - want_lse).abs().max() < 4e-3
 
 
 def test_cross_attention_matches_simt_on_same_bf16_inputs():
