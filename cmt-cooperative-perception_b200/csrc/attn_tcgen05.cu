@@ -17,22 +17,13 @@
 //   warp  8     TMA producer        : Q (64B swizzle), K tiles [128 tok x 32] (64B swizzle),
 //                                     V^T tiles [32 x 128 tok] (two 128B-swizzle boxes), 4-stage rings
 //   warp  9     MMA issuer          : S_i = Q_i K^T  (tcgen05.mma SS, M128 N128 K16 x2)
-//                                     O_i += P_i [V | 1] (tcgen05.mma TS, A = P in TMEM, M128 N48 K16 x8)
+//                                     O_i += P_i V   (tcgen05.mma TS, A = P in TMEM, M128 N32 K16 x8)
 //   warp 10     TMEM allocator
-// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,432) O1 [432,480).
+// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,416) O1 [416,448).
 //
 // Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
 // rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
 // than 2^8, so the common tile does no accumulator traffic at all.
-//
-// Row sums on the tensor pipe: every V^T stage carries 16 extra constant rows (row 32 = ones, rows
-// 33..47 = zeros), so the PV MMA (N = 48) also produces sum_j P_ij in accumulator column 32 -- from
-// exactly the bf16-rounded P the numerator uses, and without one FADD per score on the CUDA cores.
-//
-// Latency hiding: S_i(j+1) is issued as soon as warpgroup i has pulled S_i(j) into registers
-// (s_empty), not after P_i(j) -- so the next score tile is computed while the current softmax runs and
-// the MUFU pipe (the real bound at d_head = 32) is not left idle across the
-// softmax -> MMA -> softmax round trip.  pv_done_i orders P_i / O_i reuse.
 #include "kernels.cuh"
 
 namespace cmt {
@@ -41,16 +32,12 @@ namespace attn {
 constexpr int QBLK = 256;
 constexpr int KT = 128;
 constexpr int NK = 4, NV = 4;
-constexpr int TILE_BYTES = 128 * 32 * 2;       // 8 KB: one Q tile or one K tile
-constexpr int V_BOX_BYTES = 48 * 128;          // 32 TMA rows (d) + 16 constant rows, 64 tokens (128 B) wide
-constexpr int V_STAGE_BYTES = 2 * V_BOX_BYTES; // two 64-token boxes per 128-token tile
-constexpr int V_TMA_BYTES = 2 * 32 * 128;      // bytes TMA delivers per stage
-constexpr int ON = 48;                         // PV accumulator columns: 32 (O) + 1 (row sum) + 15 (zero)
+constexpr int TILE_BYTES = 128 * 32 * 2;  // 8 KB: one Q tile, one K tile, one V^T tile
 constexpr int THREADS = 384;
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
 constexpr int OFF_V = OFF_K + NK * TILE_BYTES;
-constexpr int OFF_BAR = OFF_V + NV * V_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_V + NV * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;
@@ -61,33 +48,11 @@ struct TcAttnParams {
     int kv_begin, kv_end;
     int T;            // KV tile-steps per item
     int qblocks;      // ceil(Nq / 256)
-    long long W;      // B * H * T : tile-steps of one query-block column
-    int groups;       // CTA groups; group g walks range g of [0, W), its qblocks CTAs take one query block each
+    long long W;      // items * T
     int S_max;        // partial slots per item
     float* part_o;    // [items*S_max][256][32]
     float* part_lse;  // [items*S_max][256]   (log2 domain)
 };
-
-// Debug-only phase timing (tools/attn_timing.py): when set, CTA 0 accumulates clock64 deltas per wait site.
-__device__ long long* g_attn_timing = nullptr;
-#define TWAIT(slot, bar, parity)                                   \
-    do {                                                           \
-        if (tim) {                                                 \
-            const long long t0__ = clock64();                      \
-            mbar_wait(bar, parity);                                \
-            atomicAdd(reinterpret_cast<unsigned long long*>(g_attn_timing + (slot)), static_cast<unsigned long long>(clock64() - t0__)); \
-        } else {                                                   \
-            mbar_wait(bar, parity);                                \
-        }                                                          \
-    } while (0)
-#define TMARK(slot, since)                                         \
-    do {                                                           \
-        if (tim) {                                                 \
-            const long long now__ = clock64();                     \
-            atomicAdd(reinterpret_cast<unsigned long long*>(g_attn_timing + (slot)), static_cast<unsigned long long>(now__ - (since))); \
-            (since) = now__;                                       \
-        }                                                          \
-    } while (0)
 
 __device__ __forceinline__ long long range_start(long long c, long long W, long long G) {
     return (c * W) / G;
@@ -109,11 +74,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     uint64_t* k_empty = bars + 2 + NK;       // [NK]
     uint64_t* v_full = bars + 2 + 2 * NK;    // [NV]
     uint64_t* v_empty = v_full + NV;         // [NV]
-    uint64_t* s_full = v_empty + NV;         // [2]  MMA -> softmax : S_i(t) is in TMEM
-    uint64_t* s_empty = s_full + 2;          // [2]  softmax -> MMA : S_i(t) is in registers (128 arrivals)
-    uint64_t* p_full = s_empty + 2;          // [2]  softmax -> MMA : P_i(t) is in TMEM      (128 arrivals)
-    uint64_t* pv_done = p_full + 2;          // [2]  MMA -> softmax : O_i += P_i(t) V retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    uint64_t* s_full = v_empty + NV;         // [2]
+    uint64_t* p_full = s_full + 2;           // [2]
+    uint64_t* o_full = p_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -129,36 +93,20 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 128);
             mbar_init(&p_full[i], 128);
-            mbar_init(&pv_done[i], 1);
+            mbar_init(&o_full[i], 1);
         }
         fence_barrier_init();
     }
     if (warp == 10) tmem_alloc(tmem_slot, 512);
-    // constant rows of every V^T stage: row 32 = 1.0 (bf16 0x3F80), rows 33..47 = 0.  A row of identical
-    // 16-byte chunks is invariant under the 128B swizzle, so plain stores are enough.
-    for (int idx = threadIdx.x; idx < NV * 2 * 16 * 8; idx += THREADS) {
-        const int chunk = idx & 7, row = (idx >> 3) & 15, box = (idx >> 7) & 1, stage = idx >> 8;
-        const uint32_t v = (row == 0) ? 0x3F803F80u : 0u;
-        uint4* dst = reinterpret_cast<uint4*>(smem + OFF_V + stage * V_STAGE_BYTES + box * V_BOX_BYTES +
-                                              (32 + row) * 128 + chunk * 16);
-        *dst = make_uint4(v, v, v, v);
-    }
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // The qblocks CTAs of a group stream the SAME K / V^T tiles at the same time, one 256-query block
-    // each, so a tile is fetched from HBM once and served to the other CTAs of the group from L2.
-    const bool tim = (g_attn_timing != nullptr) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 8);
-    const long long G = p.groups;
-    const int qb = static_cast<int>(blockIdx.x) % p.qblocks;
-    const long long grp = static_cast<long long>(blockIdx.x) / p.qblocks;
-    const long long pos_begin = grp < G ? range_start(grp, p.W, G) : 0;
-    const long long pos_end = grp < G ? range_start(grp + 1, p.W, G) : 0;
+    const long long G = gridDim.x;
+    const long long pos_begin = range_start(blockIdx.x, p.W, G);
+    const long long pos_end = range_start(blockIdx.x + 1, p.W, G);
 
     if (warp >= 8) {
         setmaxnreg_dec<80>();
@@ -169,24 +117,25 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                 const int item = static_cast<int>(pos / p.T);
                 const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
                 const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-                const int h = item % p.H;
-                const int b = item / p.H;
-                TWAIT(18, q_empty, (seg & 1) ^ 1);
+                const int qb = item % p.qblocks;
+                const int h = (item / p.qblocks) % p.H;
+                const int b = item / (p.qblocks * p.H);
+                mbar_wait(q_empty, (seg & 1) ^ 1);
                 mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
                 tma_load_4d(smem + OFF_Q, &tma_q, q_full, 0, qb * QBLK, h, b);
                 tma_load_4d(smem + OFF_Q + TILE_BYTES, &tma_q, q_full, 0, qb * QBLK + 128, h, b);
                 for (int jj = 0; jj < n; ++jj) {
                     const int tok0 = p.kv_begin + (j0 + jj) * KT;
                     const uint32_t ks = kc % NK, vs = vc % NV;
-                    TWAIT(16, &k_empty[ks], ((kc / NK) & 1) ^ 1);
+                    mbar_wait(&k_empty[ks], ((kc / NK) & 1) ^ 1);
                     mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
                     tma_load_4d(smem + OFF_K + ks * TILE_BYTES, &tma_k, &k_full[ks], 0, tok0, h, b);
                     ++kc;
-                    TWAIT(17, &v_empty[vs], ((vc / NV) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&v_full[vs], V_TMA_BYTES);
-                    uint8_t* sv = smem + OFF_V + vs * V_STAGE_BYTES;
+                    mbar_wait(&v_empty[vs], ((vc / NV) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                    uint8_t* sv = smem + OFF_V + vs * TILE_BYTES;
                     tma_load_4d(sv, &tma_v, &v_full[vs], tok0, 0, h, b);
-                    tma_load_4d(sv + V_BOX_BYTES, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
+                    tma_load_4d(sv + TILE_BYTES / 2, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
                     ++vc;
                 }
                 pos += n;
@@ -195,70 +144,67 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         } else if (warp == 9 && lane == 0) {
             // ------------------------------ MMA issuer ------------------------------
             constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, ON);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
             const uint32_t sq = smem_u32(smem + OFF_Q);
             uint32_t kc = 0, vc = 0, seg = 0;
-            uint32_t p_cnt[2] = {0, 0};   // P_i tiles consumed
-            uint32_t s_cnt[2] = {0, 0};   // S_i tiles issued
-            auto issue_s = [&](int i, uint64_t kdesc) {
-                // S_i may only be overwritten once warpgroup i holds the previous tile in registers
-                if (s_cnt[i] > 0) {
-                    TWAIT(9 + i, &s_empty[i], (s_cnt[i] - 1) & 1);
-                    tc_fence_after();
-                }
-                const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
-                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
-                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
-                tc_commit(&s_full[i]);
-                ++s_cnt[i];
-            };
+            uint32_t p_cnt[2] = {0, 0};
             for (long long pos = pos_begin; pos < pos_end;) {
                 const int item = static_cast<int>(pos / p.T);
                 const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
                 const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-                TWAIT(15, q_full, seg & 1);
+                mbar_wait(q_full, seg & 1);
                 {
                     const uint32_t ks = kc % NK;
-                    TWAIT(8, &k_full[ks], (kc / NK) & 1);
+                    mbar_wait(&k_full[ks], (kc / NK) & 1);
                     tc_fence_after();
                     const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
-                    issue_s(0, kdesc);
-                    issue_s(1, kdesc);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                        tc_commit(&s_full[i]);
+                    }
                     tc_commit(&k_empty[ks]);
                     ++kc;
                     if (n == 1) tc_commit(q_empty);
                 }
                 for (int jj = 0; jj < n; ++jj) {
-                    if (jj + 1 < n) {  // next score tiles first: they overlap the running softmax
-                        const uint32_t ks = kc % NK;
-                        TWAIT(8, &k_full[ks], (kc / NK) & 1);
-                        tc_fence_after();
-                        const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
-                        issue_s(0, kdesc);
-                        issue_s(1, kdesc);
-                        tc_commit(&k_empty[ks]);
-                        ++kc;
-                        if (jj + 2 == n) tc_commit(q_empty);
-                    }
+                    const bool has_next = (jj + 1 < n);
                     const uint32_t vs = vc % NV;
-                    TWAIT(11, &v_full[vs], (vc / NV) & 1);
+                    mbar_wait(&v_full[vs], (vc / NV) & 1);
+                    const uint32_t ks = kc % NK;
+                    if (has_next) mbar_wait(&k_full[ks], (kc / NK) & 1);
                     tc_fence_after();
-                    const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * V_STAGE_BYTES), 128);
+                    const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * TILE_BYTES), 128);
+                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        TWAIT(12 + i, &p_full[i], p_cnt[i] & 1);
+                        mbar_wait(&p_full[i], p_cnt[i] & 1);
                         ++p_cnt[i];
                         tc_fence_after();
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk) {
-                            const uint64_t vd = vdesc + (((kk >> 2) * V_BOX_BYTES + (kk & 3) * 32) >> 4);
-                            tc_mma_ts(tmem_base + COL_O + i * ON, tmem_base + COL_P + i * 64 + kk * 8, vd, idesc_o,
-                                      (jj > 0 || kk > 0) ? 1u : 0u);
+                            const uint64_t vd = vdesc + (((kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32) >> 4);
+                            tc_mma_ts(tmem_base + COL_O + i * 32, tmem_base + COL_P + i * 64 + kk * 8, vd,
+                                      idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
                         }
-                        tc_commit(&pv_done[i]);
+                        if (has_next) {
+                            const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                            tc_commit(&s_full[i]);
+                        } else {
+                            tc_commit(&o_full[i]);
+                        }
                     }
                     tc_commit(&v_empty[vs]);
                     ++vc;
+                    if (has_next) {
+                        tc_commit(&k_empty[ks]);
+                        ++kc;
+                        if (jj + 2 == n) tc_commit(q_empty);
+                    }
                 }
                 pos += n;
                 ++seg;
@@ -272,17 +218,16 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t t_s = tmem_base + lane_base + COL_S + wg * 128;
         const uint32_t t_p = tmem_base + lane_base + COL_P + wg * 64;
-        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * ON;
-        uint32_t t = 0;  // tiles processed by this warpgroup == phase index of its four barriers
+        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
+        uint32_t tile_cnt = 0, seg = 0;
         for (long long pos = pos_begin; pos < pos_end;) {
             const int item = static_cast<int>(pos / p.T);
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-            float m = -INFINITY;
-            for (int jj = 0; jj < n; ++jj, ++t) {
-                long long tphase = tim ? clock64() : 0;
-                TWAIT(0, &s_full[wg], t & 1);
-                if (tim) tphase = clock64();
+            float m = -INFINITY, l = 0.0f;
+            for (int jj = 0; jj < n; ++jj) {
+                mbar_wait(&s_full[wg], tile_cnt & 1);
+                ++tile_cnt;
                 tc_fence_after();
                 uint32_t s[4][32];
                 tmem_ld32(t_s + 0, s[0]);
@@ -290,9 +235,6 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                 tmem_ld32(t_s + 64, s[2]);
                 tmem_ld32(t_s + 96, s[3]);
                 tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(&s_empty[wg]);  // the MMA warp may now overwrite S with the next tile
-                TMARK(1, tphase);
                 const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
                 if (valid < KT) {
 #pragma unroll
@@ -310,66 +252,49 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                     mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
                 }
                 const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                TMARK(2, tphase);
-                bool pv_waited = (jj == 0);  // first tile of a segment: the previous epilogue already waited
                 if (jj == 0) {
                     m = mx;  // O_i is overwritten by the first PV of the segment: nothing to rescale
                 } else {
                     const bool need = (mx - m) > RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, need)) {
-                        // rare: O_i is ours again only once the previous PV retired
-                        mbar_wait(&pv_done[wg], (t - 1) & 1);
-                        tc_fence_after();
-                        pv_waited = true;
                         const float m_new = need ? mx : m;
                         const float alpha = ex2_approx(m - m_new);
+                        l *= alpha;
                         uint32_t o[32];
                         tmem_ld32(t_o, o);
-                        uint32_t rs = tmem_ld1(t_o + 32);
                         tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        rs = __float_as_uint(__uint_as_float(rs) * alpha);
                         tmem_st32(t_o, o);
-                        tmem_st1(t_o + 32, rs);
                         m = m_new;
                     }
                 }
-                // all 128 exponentials first (the MUFU phase overlaps the previous PV's round trip) ...
-                uint32_t pk[4][16];
+                float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m);
                         const float e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m);
-                        pk[c][i] = pack_bf16x2(e0, e1);
+                        l0 += e0;
+                        l1 += e1;
+                        pk[i] = pack_bf16x2(e0, e1);
                     }
+                    tmem_st16(t_p + c * 16, pk);
                 }
-                // ... then P_i(t-1) must have been consumed before P_i(t) overwrites it
-                TMARK(3, tphase);
-                if (!pv_waited) {
-                    mbar_wait(&pv_done[wg], (t - 1) & 1);
-                    tc_fence_after();
-                }
-                TMARK(4, tphase);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_st16(t_p + c * 16, pk[c]);
+                l += l0 + l1;
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&p_full[wg]);
-                TMARK(5, tphase);
-                if (tim) atomicAdd(reinterpret_cast<unsigned long long*>(g_attn_timing + 6), 1ull);
             }
             // segment epilogue: normalised partial + log2-sum-exp into the workspace
-            mbar_wait(&pv_done[wg], (t - 1) & 1);
+            mbar_wait(&o_full[wg], seg & 1);
             tc_fence_after();
             uint32_t o[32];
             tmem_ld32(t_o, o);
-            const float l = __uint_as_float(tmem_ld1(t_o + 32));  // row sum from the ones column
             tc_wait_ld();
-            const int slot = (item * p.qblocks + qb) * p.S_max +
-                             (static_cast<int>(grp) - cta_of(static_cast<long long>(item) * p.T, p.W, G));
+            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(static_cast<long long>(item) * p.T, p.W, G));
             const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
             const float inv = 1.0f / l;
             float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
@@ -380,6 +305,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             p.part_lse[prow] = m + log2f(l);
             tc_fence_before();
             pos += n;
+            ++seg;
         }
     }
 
@@ -407,7 +333,7 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
         const int b = item / (p.qblocks * p.H);
         const int row = qb * attn::QBLK + rr;
         if (row >= p.Nq) continue;
-        const long long x0 = static_cast<long long>(item / p.qblocks) * p.T;
+        const long long x0 = static_cast<long long>(item) * p.T;
         const int nseg = cta_of(x0 + p.T - 1, p.W, G) - cta_of(x0, p.W, G) + 1;
         float mx = -INFINITY;
         for (int s = 0; s < nseg; ++s)
@@ -443,20 +369,17 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
 static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid) {
     p->qblocks = (Nq + attn::QBLK - 1) / attn::QBLK;
     p->T = (n_tok + attn::KT - 1) / attn::KT;
-    p->W = static_cast<long long>(B) * H * p->T;
-    long long G = sms / p->qblocks;
+    const long long items = static_cast<long long>(B) * H * p->qblocks;
+    p->W = items * p->T;
+    long long G = sms;
     if (G > p->W) G = p->W;
     if (G < 1) G = 1;
     const long long chunk_min = p->W / G;  // >= 1
     p->S_max = static_cast<int>((p->T - 1) / chunk_min + 2);
-    p->groups = static_cast<int>(G);
-    *grid = static_cast<int>(G) * p->qblocks;
+    *grid = static_cast<int>(G);
 }
 
-int tc_attn_set_timing_buffer(long long* dev_buf) {
-    cudaError_t e = cudaMemcpyToSymbol(g_attn_timing, &dev_buf, sizeof(dev_buf));
-    return e == cudaSuccess ? CMT_OK : cuda_fail(e, "tc_attn_set_timing_buffer");
-}
+int tc_attn_set_timing_buffer(long long*) { return CMT_OK; }  // phase-timing hook of the experimental builds (unused)
 
 size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
@@ -531,9 +454,9 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     const long long cap = static_cast<long long>(device_sm_count()) * 8;
     if (mblocks > cap) mblocks = cap;
     if (a.o_bf16)
-        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, p.groups, a.o, a.lse);
+        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
     else
-        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, p.groups, a.o, a.lse);
+        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(merge)");
     return CMT_OK;
 }

@@ -107,11 +107,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > CMT_SPIN_LIMIT) {
-            printf("cmtcoop_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
-                   static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x), smem_u32(bar), parity);
-            __trap();
-        }
+        if (++spins > CMT_SPIN_LIMIT) __trap();  // surfaces as cudaErrorLaunchFailure
     }
 }
 
