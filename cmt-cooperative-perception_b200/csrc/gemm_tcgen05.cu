@@ -147,10 +147,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+            // column-block addressing without a 64-bit division per chunk: one division per tile, then the
+            // (block, offset-in-block) pair advances by 32 columns per chunk
+            const int c_first = half * (BN / 64);
+            const long long n_first = static_cast<long long>(nt) * BN + c_first * 32;
+            long long blk = n_first / p.cb;
+            long long rem = n_first - blk * p.cb;
+            const long long row_off = z * p.strideC + static_cast<long long>(m) * p.ldc;
 #pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            for (int c = c_first; c < c_first + BN / 64; ++c) {
                 const int n0 = nt * BN + c * 32;
                 if (n0 >= p.N) break;  // warp-uniform
+                const long long off = row_off + blk * p.cb_stride + rem;
+                rem += 32;
+                if (rem >= p.cb) { rem -= p.cb; ++blk; }
                 uint32_t v[32];
                 tmem_ld32(t_row + c * 32, v);
                 const bool full = (n0 + 32 <= p.N);
@@ -183,8 +193,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
                 }
                 if (m_ok) {
-                    const long long off = z * p.strideC + (n0 / p.cb) * p.cb_stride +
-                                          static_cast<long long>(m) * p.ldc + (n0 % p.cb);
                     if (p.out_bf16) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
                         if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {

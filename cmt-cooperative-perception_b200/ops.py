@@ -240,7 +240,8 @@ def _workspace(dev, nbytes):
     return buf
 
 
-def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False):
+def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False,
+               tag="cross_attn"):
     """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
     vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq])."""
     q = _cuda(q, "q")
@@ -267,7 +268,7 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         with torch.cuda.device(q.device):
             ws_bytes = int(lib.cmt_cross_attn_workspace_bytes(B, H, Nq, kv_end - kv_begin))
         ws = _workspace(q.device, ws_bytes)
-    ev = _profile.get("cross_attn")
+    ev = _profile.get(tag)
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -71,6 +71,8 @@ class SeparateTaskHead(nn.Module):
         self.heads = heads
         self.groups = groups
         self.init_bias = init_bias
+        self._kernel_size = final_kernel
+        self._two_stage = all(v[1] == 2 for v in heads.values())
         for head in self.heads:
             classes, num_conv = self.heads[head]
             layers, c_in = [], in_channels
@@ -93,8 +95,49 @@ class SeparateTaskHead(nn.Module):
             if head == "cls_logits":
                 getattr(self, head)[-1].bias.data.fill_(self.init_bias)
 
+    def _k1_weights(self):
+        """final_kernel == 1: the grouped 1x1 Conv1d pairs are per-decoder-layer GEMMs.  Stack the six heads:
+        W1 [L, H*64, C], LN affine [L, 1, H, 64], W2 [L, H, cmax, 64] (zero padded), b2 [L, 1, H, cmax]."""
+        names = list(self.heads)
+        seqs = [getattr(self, n) for n in names]
+        key = tuple((s[0].weight._version, s[0].weight.data_ptr(), s[1].weight._version, s[1].bias._version,
+                     s[3].weight._version, s[3].bias._version) for s in seqs)
+        hit = self.__dict__.get("_k1_cache")
+        if hit is None or hit[0] != key:
+            L = self.groups
+            hc = seqs[0][0].weight.shape[0] // L
+            C = seqs[0][0].weight.shape[1]
+            couts = [s[3].weight.shape[0] // L for s in seqs]
+            cmax = max(couts)
+            w1 = torch.stack([s[0].weight.detach().view(L, hc, C) for s in seqs], 1).reshape(L, len(seqs) * hc, C)
+            g = torch.stack([s[1].weight.detach().view(L, hc) for s in seqs], 1).unsqueeze(1)
+            b = torch.stack([s[1].bias.detach().view(L, hc) for s in seqs], 1).unsqueeze(1)
+            w2 = w1.new_zeros(L, len(seqs), cmax, hc)
+            b2 = w1.new_zeros(L, 1, len(seqs), cmax)
+            for i, (s, co) in enumerate(zip(seqs, couts)):
+                w2[:, i, :co] = s[3].weight.detach().view(L, co, hc)
+                b2[:, 0, i, :co] = s[3].bias.detach().view(L, co)
+            hit = (key, (names, couts, hc, w1.transpose(1, 2).contiguous(), g, b, w2, b2, seqs[0][1].eps))
+            self.__dict__["_k1_cache"] = hit
+        return hit[1]
+
+    def _forward_k1(self, x):
+        """Same arithmetic as the Conv1d(k=1, groups=L) -> GroupLayerNorm1d -> ReLU -> Conv1d(k=1, groups=L)
+        stacks (cmt_head.py:116-150), as 1 bmm + 1 fused LN + 1 einsum for all six outputs instead of
+        ~250 cuDNN launches."""
+        L, B, Q, C = x.shape
+        names, couts, hc, w1t, g, b, w2, b2, eps = self._k1_weights()
+        h = torch.bmm(x.reshape(L, B * Q, C), w1t).view(L, B * Q, len(names), hc)
+        mu = h.mean(-1, keepdim=True)
+        var = (h - mu).pow(2).mean(-1, keepdim=True)
+        y = torch.relu((h - mu) / (var + eps).sqrt() * g + b)
+        out = torch.einsum("lmhc,lhoc->lmho", y, w2) + b2
+        return {n: out[:, :, i, :co].reshape(L, B, Q, co) for i, (n, co) in enumerate(zip(names, couts))}
+
     def forward(self, x):
         N, B, Q, C = x.shape
+        if self._kernel_size == 1 and self._two_stage and not self.training:
+            return self._forward_k1(x)
         x = x.permute(1, 0, 3, 2).reshape(B, N * C, Q)  # "n b q c -> b (n c) q"
         ret = {}
         for head in self.heads:

@@ -107,7 +107,7 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
         q = ops.linear(xq_lp, sw["wq"], sw["bq"], alpha=_Q_SCALE, out_dtype=dt)
         k = ops.project_keys(xq_lp, sw["wk"], sw["bk"], 1, H)
         vt = ops.project_values_t(x_lp, sw["wv"], sw["bv"], 1, H)
-        ctx = ops.cross_attn(q, k, vt, 0)
+        ctx = ops.cross_attn(q, k, vt, 0, tag="self_attn")
         sa = ops.linear(ctx, sw["wo"], sw["bo"], out_dtype=torch.float32)
         g, b, eps = _ln(layer.norms[0])
         x1, _, _, x1q_lp = ops.add_layernorm(x, sa, g, b, eps, add=query_pos, lp_dtype=dt, want_yadd=True)

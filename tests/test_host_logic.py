@@ -76,7 +76,8 @@ def test_task_heads_and_coder_match_oracle_cpu():
         with torch.no_grad():
             got = head._finish(outs_dec, ref)
         for name in want[0]:
-            assert torch.allclose(got[0][name], want[0][name], atol=1e-5, rtol=1e-5), (kind, name)
+            # fp32 both sides; the k=1 heads run as batched GEMMs (different summation order than conv1d)
+            assert torch.allclose(got[0][name], want[0][name], atol=2e-4, rtol=1e-4), (kind, name)
         wb = O.bbox_decode(want, cfg)
         gb = head.bbox_coder.decode([[got[0]]])
         for i in range(2):
