@@ -154,19 +154,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             long long blk = n_first / p.cb;
             long long rem = n_first - blk * p.cb;
             const long long row_off = z * p.strideC + static_cast<long long>(m) * p.ldc;
-#pragma unroll 1
-            for (int c = c_first; c < c_first + BN / 64; ++c) {
-                const int n0 = nt * BN + c * 32;
-                if (n0 >= p.N) break;  // warp-uniform
-                const long long off = row_off + blk * p.cb_stride + rem;
-                rem += 32;
-                if (rem >= p.cb) { rem -= p.cb; ++blk; }
-                uint32_t v[32];
-                tmem_ld32(t_row + c * 32, v);
-                const bool full = (n0 + 32 <= p.N);
-                float f[32];
+            // bias for one 32-column chunk (independent of the accumulator: issued before the TMEM wait)
+            auto load_bias = [&](int n0, float (&f)[32]) {
                 if (col_bias) {
-                    if (full) {
+                    if (n0 + 32 <= p.N) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);  // n0 % 32 == 0
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -181,7 +172,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = row_bias;
                 }
-                tc_wait_ld();
+            };
+            auto finish = [&](int n0, long long off, const uint32_t (&v)[32], float (&f)[32]) {
+                const bool full = (n0 + 32 <= p.N);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
                 if (scale) {
@@ -192,36 +185,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
                 }
-                if (m_ok) {
-                    if (p.out_bf16) {
-                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                if (!m_ok) return;
+                if (p.out_bf16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+                    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                uint4 w;
-                                w.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-                                w.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-                                w.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-                                w.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-                                reinterpret_cast<uint4*>(dst)[i] = w;
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (n0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 w;
+                            w.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                            w.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                            w.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                            w.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                            reinterpret_cast<uint4*>(dst)[i] = w;
                         }
                     } else {
-                        float* dst = reinterpret_cast<float*>(p.C) + off;
-                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.C) + off;
+                    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                reinterpret_cast<float4*>(dst)[i] =
-                                    make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (n0 + i < p.N) dst[i] = f[i];
-                        }
+                        for (int i = 0; i < 8; ++i)
+                            reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) dst[i] = f[i];
                     }
                 }
+            };
+            // two 32-column chunks per round: both TMEM loads and both bias fetches are in flight together
+#pragma unroll 1
+            for (int c = c_first; c < c_first + BN / 64; c += 2) {
+                const int n0a = nt * BN + c * 32, n0b = n0a + 32;
+                if (n0a >= p.N) break;  // warp-uniform
+                const bool has_b = n0b < p.N;
+                const long long offa = row_off + blk * p.cb_stride + rem;
+                rem += 32;
+                if (rem >= p.cb) { rem -= p.cb; ++blk; }
+                const long long offb = row_off + blk * p.cb_stride + rem;
+                rem += 32;
+                if (rem >= p.cb) { rem -= p.cb; ++blk; }
+                uint32_t va[32], vb[32];
+                float fa[32], fb[32];
+                tmem_ld32(t_row + c * 32, va);
+                if (has_b) tmem_ld32(t_row + (c + 1) * 32, vb);
+                load_bias(n0a, fa);
+                if (has_b) load_bias(n0b, fb);
+                tc_wait_ld();
+                finish(n0a, offa, va, fa);
+                if (has_b) finish(n0b, offb, vb, fb);
             }
             tc_fence_before();
             __syncwarp();

@@ -1,0 +1,90 @@
+"""Serving-loop helper: run a head over a stream of HOST batches with the host->device copy of batch
+i+1 and the device->host copy of result i-1 overlapped with the compute of batch i.
+
+The hot path itself never synchronises (every kernel is stream-ordered), so overlapping is a matter of
+three CUDA streams and double buffering:
+
+    copy-in stream : pinned host features -> device buffer[i % 2]
+    compute stream : head.forward_single(device buffer[i % 2]) -> task-head tensors
+    copy-out stream: task-head tensors -> pinned host result[i % 2]
+
+This is plumbing (torch streams / events), not a kernel; it is what bench.py's end-to-end number uses.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class PipelinedRunner:
+    def __init__(self, head, img_metas, example_inputs: dict, device):
+        """example_inputs: {name: pinned CPU tensor} with the feature tensors `forward_single` takes
+        (pts_feats / img_feats, or the four vehicle_/infrastructure_ entries for the coop heads)."""
+        self.head = head
+        self.metas = img_metas
+        self.dev = torch.device(device)
+        self.coop = type(head).__name__.endswith("Coop")
+        self.keys = list(example_inputs.keys())
+        self.dbuf = [{k: torch.empty_like(v, device=self.dev) for k, v in example_inputs.items()} for _ in range(2)]
+        self.hout = [None, None]
+        self.s_in = torch.cuda.Stream(self.dev)
+        self.s_out = torch.cuda.Stream(self.dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]       # copy-in of slot done
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading slot
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]     # compute of slot done
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]      # copy-out of slot done
+        self._primed = [False, False]
+        self.h2d_bytes = int(sum(v.numel() * v.element_size() for v in example_inputs.values()))
+        self.d2h_bytes = 0
+
+    def _forward(self, feats):
+        g = feats.get
+        if self.coop:
+            return self.head.forward_single(g("vehicle_pts_feats"), g("infrastructure_pts_feats"),
+                                            g("vehicle_img_feats"), g("infrastructure_img_feats"), self.metas)
+        return self.head.forward_single(g("pts_feats"), g("img_feats"), self.metas)
+
+    def _enqueue_copy_in(self, slot, host_inputs):
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            if self._primed[slot]:
+                self.s_in.wait_event(self.ev_free[slot])   # the previous user of this slot has consumed it
+            for k in self.keys:
+                self.dbuf[slot][k].copy_(host_inputs[k], non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        del cur
+
+    @torch.no_grad()
+    def run(self, host_batches):
+        """host_batches: iterable of {name: pinned CPU tensor}.  Returns the list of per-batch results
+        (dicts of pinned CPU tensors, valid after the final synchronize this method performs)."""
+        cur = torch.cuda.current_stream(self.dev)
+        batches = list(host_batches)
+        results = []
+        if not batches:
+            return results
+        self._enqueue_copy_in(0, batches[0])
+        for i, _ in enumerate(batches):
+            slot = i & 1
+            if i + 1 < len(batches):
+                self._enqueue_copy_in(slot ^ 1, batches[i + 1])     # overlaps this step's compute
+            cur.wait_event(self.ev_in[slot])
+            if self.hout[slot] is not None:
+                cur.wait_event(self.ev_out[slot])                   # result buffers of this slot are free again
+            rets = self._forward(self.dbuf[slot])
+            self.ev_free[slot].record(cur)
+            self._primed[slot] = True
+            outs = rets[0]
+            if self.hout[slot] is None:
+                self.hout[slot] = {n: torch.empty(t.shape, dtype=t.dtype).pin_memory() for n, t in outs.items()}
+                self.d2h_bytes = int(sum(t.numel() * t.element_size() for t in outs.values()))
+            self.ev_done[slot].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_done[slot])
+                for n, t in outs.items():
+                    t.record_stream(self.s_out)
+                    self.hout[slot][n].copy_(t, non_blocking=True)
+                self.ev_out[slot].record(self.s_out)
+            results.append(self.hout[slot])
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_in)
+        return results
