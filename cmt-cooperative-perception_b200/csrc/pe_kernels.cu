@@ -13,57 +13,83 @@ namespace cmt {
 struct RayPeParams {
     float pc_min[3];
     float pc_rng[3];
+    float pc_inv[3];       // float(1 / pc_rng) for the 3-instruction correctly rounded division
     float depth_step_num;  // (pc_range[3] - 1)
     float pad_h, pad_w;
     int n_cam, H, W, D;
 };
 
-// One thread = 8 consecutive output features of one pixel (one 16-byte bf16 store or two
-// 16-byte fp32 stores), so a warp writes 512 (bf16) / 1024 (fp32) contiguous bytes.
+// Correctly rounded a / b for normal operands given inv = float(1 / b): one residual correction of the
+// reciprocal product (3 instructions instead of the ~15 of the generic IEEE division sequence).
+__device__ __forceinline__ float div_by_const(float a, float b, float inv) {
+    const float q = a * inv;
+    const float r = fmaf(-q, b, a);
+    return fmaf(r, inv, q);
+}
+
+// One block = one feature-map row of one camera (W pixels x D*3 features, contiguous in the output);
+// one thread-item = 8 consecutive depth bins x 3 coordinates = 24 consecutive features of one pixel
+// (48 bytes bf16 / 96 bytes fp32, written as 16-byte vectors; a warp covers 1536 / 3072 contiguous bytes).
+// With that unit every index is a compile-time constant: the camera matrix and pc_range constants sit in
+// registers, depth bins and pixel abscissae come from two small shared-memory tables (filled with true
+// divisions once per block), and the normalising division is a 3-instruction correctly rounded sequence.
+// ~9 instructions per output value, so the kernel is bound by the HBM write instead of by issue.
 template <bool kBf16>
 __global__ void __launch_bounds__(256) ray_pe_kernel(const float* __restrict__ img2lidar,
                                                      void* __restrict__ out, RayPeParams p) {
-    const int feats = p.D * 3;
-    const int groups = feats >> 3;  // feats % 8 == 0 is checked on the host
-    const long long total = static_cast<long long>(p.n_cam) * p.H * p.W * groups;
-    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
-         t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(t % groups);
-        const long long pix = t / groups;
-        const int j = static_cast<int>(pix % p.W);
-        const int i = static_cast<int>((pix / p.W) % p.H);
-        const int cam = static_cast<int>(pix / (static_cast<long long>(p.W) * p.H));
-        const float* M = img2lidar + cam * 16;
-        // coords_w = arange(W) * pad_w / W ; coords_h = arange(H) * pad_h / H   (cmt_head.py:420-421)
-        const float u = (static_cast<float>(j) * p.pad_w) / static_cast<float>(p.W);
-        const float v = (static_cast<float>(i) * p.pad_h) / static_cast<float>(p.H);
-        float vals[8];
+    extern __shared__ float sm[];
+    float* dtab = sm;            // [D]   coords_d = 1 + arange(D) * (pc_range[3] - 1) / D      (cmt_head.py:422)
+    float* utab = sm + p.D;      // [W]   coords_w = arange(W) * pad_w / W                      (cmt_head.py:421)
+    const int cam = blockIdx.x / p.H;
+    const int i = blockIdx.x - cam * p.H;
+    for (int k = threadIdx.x; k < p.D; k += blockDim.x)
+        dtab[k] = 1.0f + (static_cast<float>(k) * p.depth_step_num) / static_cast<float>(p.D);
+    for (int j = threadIdx.x; j < p.W; j += blockDim.x)
+        utab[j] = (static_cast<float>(j) * p.pad_w) / static_cast<float>(p.W);
+    float M[3][4];               // rows 0..2 of float32(inv(lidar2img))                          (cmt_head.py:428-429)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int f = g * 8 + e;
-            const int k = f / 3;
-            const int c = f - 3 * k;
-            // coords_d = 1 + arange(D) * (pc_range[3] - 1) / D                     (cmt_head.py:422)
-            const float d = 1.0f + (static_cast<float>(k) * p.depth_step_num) / static_cast<float>(p.D);
-            const float x0 = u * d, x1 = v * d;  // coords[..., :2] *= coords[..., 2:3]  (:426)
-            const float* r = M + c * 4;
-            float acc = x0 * __ldg(r + 0);
-            acc = fmaf(x1, __ldg(r + 1), acc);
-            acc = fmaf(d, __ldg(r + 2), acc);
-            acc = acc + __ldg(r + 3);
-            vals[e] = (acc - p.pc_min[c]) / p.pc_rng[c];  // (:431-432)
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) M[c][o] = __ldg(img2lidar + cam * 16 + c * 4 + o);
+    __syncthreads();
+    const float v = (static_cast<float>(i) * p.pad_h) / static_cast<float>(p.H);  // coords_h (cmt_head.py:420)
+    const int units = p.D >> 3;  // 8-bin units per pixel
+    const int items = p.W * units;
+    const long long row_base = static_cast<long long>(blockIdx.x) * items;
+    for (int tl = threadIdx.x; tl < items; tl += blockDim.x) {
+        const int j = tl / units;
+        const int k0 = (tl - j * units) << 3;
+        const float u = utab[j];
+        float vals[24];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float d = dtab[k0 + kk];
+            const float x0 = u * d, x1 = v * d;  // coords[..., :2] *= coords[..., 2:3]   (cmt_head.py:426)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float acc = x0 * M[c][0];
+                acc = fmaf(x1, M[c][1], acc);
+                acc = fmaf(d, M[c][2], acc);
+                acc = acc + M[c][3];
+                vals[kk * 3 + c] = div_by_const(acc - p.pc_min[c], p.pc_rng[c], p.pc_inv[c]);  // (:431-432)
+            }
         }
+        const long long t = row_base + tl;  // in 24-feature units
         if (kBf16) {
-            uint4 w;
-            w.x = pack_bf16x2(vals[0], vals[1]);
-            w.y = pack_bf16x2(vals[2], vals[3]);
-            w.z = pack_bf16x2(vals[4], vals[5]);
-            w.w = pack_bf16x2(vals[6], vals[7]);
-            reinterpret_cast<uint4*>(out)[t] = w;
+            uint4* o = reinterpret_cast<uint4*>(out) + 3 * t;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                uint4 w;
+                w.x = pack_bf16x2(vals[8 * q + 0], vals[8 * q + 1]);
+                w.y = pack_bf16x2(vals[8 * q + 2], vals[8 * q + 3]);
+                w.z = pack_bf16x2(vals[8 * q + 4], vals[8 * q + 5]);
+                w.w = pack_bf16x2(vals[8 * q + 6], vals[8 * q + 7]);
+                o[q] = w;
+            }
         } else {
-            float4* o = reinterpret_cast<float4*>(out) + 2 * t;
-            o[0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
-            o[1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
+            float4* o = reinterpret_cast<float4*>(out) + 6 * t;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
         }
     }
 }
@@ -205,12 +231,13 @@ int launch_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, in
                   float pad_w, const float* pc, int out_dtype, cudaStream_t stream) {
     CMT_CHECK_ARG(img2lidar && out && pc, "cmt_ray_pe: null pointer");
     CMT_CHECK_ARG(n_cam > 0 && H > 0 && W > 0 && D > 0, "cmt_ray_pe: bad shape");
-    CMT_CHECK_ARG((D * 3) % 8 == 0, "cmt_ray_pe: depth_num*3 must be a multiple of 8 (got D=%d)", D);
+    CMT_CHECK_ARG(D % 8 == 0, "cmt_ray_pe: depth_num must be a multiple of 8 (got D=%d)", D);
     CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_ray_pe: bad dtype");
     RayPeParams p{};
     for (int c = 0; c < 3; ++c) {
         p.pc_min[c] = pc[c];
         p.pc_rng[c] = pc[c + 3] - pc[c];
+        p.pc_inv[c] = static_cast<float>(1.0 / static_cast<double>(p.pc_rng[c]));
     }
     p.depth_step_num = pc[3] - 1.0f;
     p.pad_h = pad_h;
@@ -219,12 +246,15 @@ int launch_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, in
     p.H = H;
     p.W = W;
     p.D = D;
-    const long long total = static_cast<long long>(n_cam) * H * W * (D * 3 / 8);
-    const int grid = grid_for(total, 256);
+    const long long blocks = static_cast<long long>(n_cam) * H;
+    CMT_CHECK_ARG(blocks < (1ll << 31), "cmt_ray_pe: too many feature rows");
+    const int grid = static_cast<int>(blocks);
+    const size_t smem = static_cast<size_t>(D + W) * sizeof(float);
+    CMT_CHECK_ARG(smem <= 48 * 1024, "cmt_ray_pe: W + D too large");
     if (out_dtype == CMT_BF16)
-        ray_pe_kernel<true><<<grid, 256, 0, stream>>>(img2lidar, out, p);
+        ray_pe_kernel<true><<<grid, 256, smem, stream>>>(img2lidar, out, p);
     else
-        ray_pe_kernel<false><<<grid, 256, 0, stream>>>(img2lidar, out, p);
+        ray_pe_kernel<false><<<grid, 256, smem, stream>>>(img2lidar, out, p);
     CMT_LAUNCH_CHECK("cmt_ray_pe");
     return CMT_OK;
 }
