@@ -41,7 +41,31 @@ constexpr int OFF_BAR = OFF_V + NV * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;
+// The MUFU pipe (16 ex2 / clk / SM, measured: tools/microbench/exp_throughput.cu) is the bound of this kernel
+// at d_head = 32.  One in (2 * POLY_EVERY) exponentials is evaluated with a degree-3 polynomial on the
+// FMA/ALU pipes instead (12.7 / clk / SM measured), which are otherwise ~20 % busy.  0 disables.
+// Measured r1 (B=8, 56 400 tokens): POLY_EVERY=2 -> 1.36 ms per launch vs 1.26 ms without: the softmax warps
+// are issue/latency bound before they are MUFU bound, so the extra ~7 instructions per offloaded element
+// cost more than the MUFU slot they free.  Kept as a switch for the next round's restructured softmax.
+#ifndef CMT_ATTN_POLY_EVERY
+#define CMT_ATTN_POLY_EVERY 0
+#endif
+constexpr int POLY_EVERY = CMT_ATTN_POLY_EVERY;
 }  // namespace attn
+
+// 2^x for x <= ~8 on the FMA/ALU pipes: split x = n + f, f in [-0.5, 0.5] with the 1.5*2^23 rounding trick,
+// 2^f by a cubic (relative error < 7e-4, below the 2^-9 rounding P gets anyway), 2^n by adding n to the
+// exponent field.  Inputs below -125 (masked scores are -inf) clamp to 2^-125, i.e. nothing after rounding.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;
+    const float n = t - 12582912.0f;
+    const float f = x - n;
+    float p = fmaf(f, 0.0555054f, 0.2402265f);
+    p = fmaf(p, f, 0.6931472f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 struct TcAttnParams {
     int B, H, Nq;
@@ -276,7 +300,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m);
-                        const float e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m);
+                        // every POLY_EVERY-th exponential runs on the FMA/ALU pipes instead of the MUFU
+                        const float x1 = __uint_as_float(s[c][2 * i + 1]) - m;
+                        const float e1 = (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x1) : ex2_approx(x1);
                         l0 += e0;
                         l1 += e1;
                         pk[i] = pack_bf16x2(e0, e1);

@@ -73,6 +73,11 @@ static std::once_flag g_encode_once;
 
 int encode_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    return encode_tma(map, base, CMT_BF16, rank, dims, strides_bytes, box, swizzle_bytes);
+}
+
+int encode_tma(CUtensorMap* map, const void* base, int dtype, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
     std::call_once(g_encode_once, []() {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -96,8 +101,10 @@ int encode_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
     }
     const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                        : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUtensorMapDataType dt = dtype == CMT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = g_encode(map, dt, static_cast<cuuint32_t>(rank),
                           const_cast<void*>(base), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

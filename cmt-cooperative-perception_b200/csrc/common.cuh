@@ -40,6 +40,9 @@ int require_sm100();
 int encode_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
                     int swizzle_bytes /* 64 or 128 */);
+// general form: dtype CMT_F32 | CMT_BF16, swizzle_bytes 0 (none) | 32 | 64 | 128
+int encode_tma(CUtensorMap* map, const void* base, int dtype, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ---------------------------------------------------------------------------
 // small device helpers
@@ -132,6 +135,24 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
         "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+// smem -> global tensor store (bulk async group), used by the GEMM epilogue
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1,
+                                             int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ------------------------------ tcgen05 ------------------------------------

@@ -12,6 +12,7 @@
 //
 // Replaces F.linear in models/utils/attention.py:21-27,138 and the PE MLPs of
 // models/dense_heads/cmt_head.py:292-301 (reference runs them as fp32 cuBLAS SGEMMs).
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace cmt {
@@ -22,7 +23,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STORE_STAGING = 8 * 4096;  // per epilogue warp: two 32x32 bf16 tiles or one 32x32 fp32 tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 384;  // 4 control warps + 8 epilogue warps
 }  // namespace gemm
 
@@ -34,16 +36,19 @@ struct TcGemmParams {
     float alpha;
     int relu, bias_per_row, out_bf16;
     int a_batched, b_batched;
+    int tma_store;  // epilogue through shared memory + TMA tensor store (full-sector, coalesced writes)
+    int cb32;       // column block size as int (for the store coordinates)
     int m_tiles, n_tiles, total_tiles, num_kb;
 };
 
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const TcGemmParams p) {
     using namespace gemm;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STORE_STAGING);
     uint64_t* full_bar = bars;                   // [STAGES]
     uint64_t* empty_bar = bars + STAGES;         // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
@@ -135,6 +140,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool has_bias = p.bias != nullptr;
         const bool col_bias = has_bias && !p.bias_per_row;
         const bool scale = p.alpha != 1.0f;
+        uint32_t store_cnt = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -184,6 +190,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (p.relu) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+                }
+                if (p.tma_store) {
+                    // registers -> this warp's staging tile [32 rows][32 cols] -> one TMA tensor store.
+                    // A thread's direct 16-byte stores land in 64-byte-strided rows: half-filled sectors and
+                    // 32 sectors per request; the TMA store writes whole lines and clips the M / N tails itself.
+                    uint8_t* tile = staging + (warp - 4) * 4096 + (p.out_bf16 ? (store_cnt & 1) * 2048 : 0);
+                    if (lane == 0) {
+                        if (p.out_bf16) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                    }
+                    __syncwarp();
+                    if (p.out_bf16) {
+                        uint4* row = reinterpret_cast<uint4*>(tile + lane * 64);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 w;
+                            w.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                            w.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                            w.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                            w.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                            row[i] = w;
+                        }
+                    } else {
+                        float4* row = reinterpret_cast<float4*>(tile + lane * 128);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) row[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int nb = n0 / p.cb32;
+                        tma_store_4d(&tma_c, tile, n0 - nb * p.cb32, mt * BM + quad * 32, nb, z);
+                        tma_store_commit();
+                    }
+                    ++store_cnt;
+                    return;
                 }
                 if (!m_ok) return;
                 if (p.out_bf16) {
@@ -241,6 +282,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all<0>();  // all tensor stores of this warp have landed
     }
 
     tc_fence_before();
@@ -292,7 +334,32 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
         if (rc) return rc;
     }
 
+    // C tensor map in "column block" coordinates (n % cb, m, n / cb, batch); used when the layout is TMA-able
+    CUtensorMap tc;
+    const int esz = g.out_bf16 ? 2 : 4;
+    const bool plain = g.cb >= g.N;
+    bool tma_store = (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc * esz) % 16 == 0 &&
+                     (plain || ((g.cb_stride * esz) % 16 == 0 && g.cb % 32 == 0)) &&
+                     (batch == 1 || (g.strideC * esz) % 16 == 0) && g.cb < (1ll << 31);
+    if (getenv("CMT_GEMM_NO_TMA_STORE")) tma_store = false;
+    if (tma_store) {
+        const uint64_t d0 = plain ? static_cast<uint64_t>(g.N) : static_cast<uint64_t>(g.cb);
+        const uint64_t d2 = plain ? 1 : static_cast<uint64_t>((g.N + g.cb - 1) / g.cb);
+        uint64_t dims[4] = {d0, static_cast<uint64_t>(g.M), d2, static_cast<uint64_t>(batch)};
+        uint64_t strides[3] = {static_cast<uint64_t>(g.ldc) * esz,
+                               static_cast<uint64_t>(plain ? g.M * g.ldc : g.cb_stride) * esz,
+                               static_cast<uint64_t>(batch > 1 ? g.strideC : (plain ? g.M * g.ldc : g.cb_stride * d2)) * esz};
+        uint32_t box[4] = {32, 32, 1, 1};
+        if (d0 < 32) box[0] = static_cast<uint32_t>(d0);
+        int rc = encode_tma(&tc, g.C, g.out_bf16 ? CMT_BF16 : CMT_F32, 4, dims, strides, box, 0);
+        if (rc) tma_store = false;  // fall back to direct stores (e.g. stride not encodable)
+        if (d0 < 32) tma_store = false;
+    }
+    if (!tma_store) tc = ta;  // unused placeholder
+
     TcGemmParams p{};
+    p.tma_store = tma_store ? 1 : 0;
+    p.cb32 = static_cast<int>(plain ? (1ll << 30) : g.cb);
     p.bias = g.bias;
     p.C = g.C;
     p.M = g.M;
@@ -316,7 +383,7 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     p.num_kb = (g.K + BK - 1) / BK;
     int grid = device_sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);
     CMT_LAUNCH_CHECK("cmt_gemm_bias_act(tcgen05)");
     return CMT_OK;
 }
