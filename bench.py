@@ -45,6 +45,12 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of tc_attn_kernel per launch from the committed ncu --set full
+# capture (profiles/r1_attn_gemm_ncu_raw.csv: 1.8615 GB + 0.0139 GB at B=8), per frame.  K+V of one layer are
+# 57.8 MB per frame; the 4 query blocks of a (frame, head) stream them at different times, hence 4.06x.
+NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.861532e9 + 0.013930e9) / 8}
+
+
 def build_case(workload, B, seed=0):
     kind, bev_hw, n_views, _ = WORKLOADS[workload]
     cfg = synth.head_cfg(kind, num_query=900, num_layers=6, grid=8 * bev_hw)
@@ -288,7 +294,7 @@ def main():
         achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="tc_attn_kernel(+merge)", achieved=achieved,
                     peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"],
-                    traffic=None, peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
+                    traffic=NCU_DRAM_BYTES_PER_FRAME.get(args.workload, 0) * B or None, peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
                     launches_timed=len(attn_ms), avg_launch_ms=attn_avg_ms,
                     share_of_step=attn_avg_ms * len(attn_ms) / ms,
                     algorithmic_flops_per_launch=flops_per_launch)
