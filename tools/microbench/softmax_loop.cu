@@ -1,0 +1,86 @@
+// Microbenchmark: the per-tile softmax work of the attention kernel in isolation (no MMA, no TMA):
+// each warp repeatedly loads a 32-lane x 128-column fp32 score block from TMEM, takes the row max,
+// exponentiates, packs to bf16 and stores the 64 packed columns back to TMEM.
+// Ideal (MUFU bound): warps * 128 * 32 exps / 16 per clk = 2048 cycles per iteration with 8 warps.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../cmt-cooperative-perception_b200/csrc/common.cuh"
+namespace cmt { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return -2; } }
+using namespace cmt;
+
+template <int MODE>  // 0: full; 1: no TMEM ld/st (registers only); 2: no exps (ld/max/st only); 3: chunked (max from previous tile)
+__global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32_t* sink) {
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(&slot, 512);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = slot + lane_base + (warp >> 2) * 128;          // S region of "my" query tile
+    const uint32_t t_p = slot + lane_base + 256 + (warp >> 2) * 64;     // P region
+    float m = 0.25f;
+    uint32_t acc = 0;
+    uint32_t s[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(1e-3f * (threadIdx.x + c * 32 + i));
+    if (MODE != 1) { tmem_st32(t_s, s[0]); tmem_st32(t_s + 32, s[1]); tmem_st32(t_s + 64, s[2]); tmem_st32(t_s + 96, s[3]); tc_wait_st(); }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (MODE != 1) {
+            tmem_ld32(t_s + 0, s[0]); tmem_ld32(t_s + 32, s[1]); tmem_ld32(t_s + 64, s[2]); tmem_ld32(t_s + 96, s[3]);
+            tc_wait_ld();
+        }
+        float mx0 = -1e30f, mx1 = -1e30f, mx2 = -1e30f, mx3 = -1e30f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[0][i])); mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[2][i])); mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (MODE == 3) { /* use stale m for this tile, update after */ } else if (mx - m > 8.0f) m = mx;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float e0, e1;
+                if (MODE == 2) { e0 = __uint_as_float(s[c][2 * i]) - m; e1 = __uint_as_float(s[c][2 * i + 1]) - m; }
+                else { e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m); e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m); }
+                pk[i] = pack_bf16x2(e0, e1);
+            }
+            if (MODE != 1) tmem_st16(t_p + c * 16, pk);
+            else { for (int i = 0; i < 16; ++i) acc ^= pk[i]; }
+        }
+        if (MODE != 1) tc_wait_st();
+        if (MODE == 3 && mx - m > 8.0f) m = mx;
+        if (MODE == 1) { for (int c = 0; c < 4; ++c) for (int i = 0; i < 32; ++i) s[c][i] += acc & 1; }
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (acc == 0x12345 || m == 123.f) sink[0] = acc;
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
+}
+
+int main() {
+    long long* dc; uint32_t* ds; cudaMalloc(&dc, 148 * 8); cudaMalloc(&ds, 4);
+    const int iters = 2000;
+    const char* names[4] = {"full (ld, max, exp, pack, st)", "registers only (no TMEM)", "no exp (ld, max, pack, st)", "full, stale max"};
+    for (int mode = 0; mode < 4; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            if (mode == 0) k<0><<<148, 256>>>(iters, dc, ds);
+            if (mode == 1) k<1><<<148, 256>>>(iters, dc, ds);
+            if (mode == 2) k<2><<<148, 256>>>(iters, dc, ds);
+            if (mode == 3) k<3><<<148, 256>>>(iters, dc, ds);
+            cudaDeviceSynchronize();
+        }
+        long long h[148]; cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("%-34s %8.1f cycles per tile-step (8 warps x 32 rows x 128 cols; MUFU bound = 2048)  [%s]\n", names[mode],
+               double(h[0]) / iters, cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
