@@ -3,13 +3,15 @@
 // exponentiates, packs to bf16 and stores the 64 packed columns back to TMEM.
 // Ideal (MUFU bound): warps * 128 * 32 exps / 16 per clk = 2048 cycles per iteration with 8 warps.
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../cmt-cooperative-perception_b200/csrc/common.cuh"
 namespace cmt { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return -2; } }
 using namespace cmt;
 
-template <int MODE>  // 0: full; 1: no TMEM ld/st (registers only); 2: no exps (ld/max/st only); 3: chunked (max from previous tile)
+template <int MODE, int PACK = 0>  // PACK 0: cvt.rn.bf16x2 (F2FP); 1: integer round + PRMT; 2: PRMT truncate
+// MODE 0: full; 1: no TMEM ld/st (registers only); 2: no exps (ld/max/st only); 3: chunked (max from previous tile)
 __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32_t* sink) {
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
@@ -49,7 +51,9 @@ __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32
                 float e0, e1;
                 if (MODE == 2) { e0 = __uint_as_float(s[c][2 * i]) - m; e1 = __uint_as_float(s[c][2 * i + 1]) - m; }
                 else { e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m); e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m); }
-                pk[i] = pack_bf16x2(e0, e1);
+                if (PACK == 0) pk[i] = pack_bf16x2(e0, e1);
+                else if (PACK == 1) pk[i] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
+                else pk[i] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
             }
             if (MODE != 1) tmem_st16(t_p + c * 16, pk);
             else { for (int i = 0; i < 16; ++i) acc ^= pk[i]; }
@@ -69,13 +73,19 @@ __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32
 int main() {
     long long* dc; uint32_t* ds; cudaMalloc(&dc, 148 * 8); cudaMalloc(&ds, 4);
     const int iters = 2000;
-    const char* names[4] = {"full (ld, max, exp, pack, st)", "registers only (no TMEM)", "no exp (ld, max, pack, st)", "full, stale max"};
-    for (int mode = 0; mode < 4; ++mode) {
+    const char* names[8] = {"full (ld, max, exp, pack, st)", "registers only (no TMEM)", "no exp (ld, max, pack, st)", "full, stale max",
+                            "registers only, round+PRMT pack", "registers only, PRMT truncate", "full, round+PRMT pack", "full, PRMT truncate"};
+    for (int mode = 0; mode < 8; ++mode) {
         for (int rep = 0; rep < 2; ++rep) {
-            if (mode == 0) k<0><<<148, 256>>>(iters, dc, ds);
-            if (mode == 1) k<1><<<148, 256>>>(iters, dc, ds);
-            if (mode == 2) k<2><<<148, 256>>>(iters, dc, ds);
-            if (mode == 3) k<3><<<148, 256>>>(iters, dc, ds);
+            const int th = getenv("THREADS") ? atoi(getenv("THREADS")) : 256;
+            if (mode == 0) k<0><<<148, th>>>(iters, dc, ds);
+            if (mode == 1) k<1><<<148, th>>>(iters, dc, ds);
+            if (mode == 2) k<2><<<148, th>>>(iters, dc, ds);
+            if (mode == 3) k<3><<<148, th>>>(iters, dc, ds);
+            if (mode == 4) k<1, 1><<<148, th>>>(iters, dc, ds);
+            if (mode == 5) k<1, 2><<<148, th>>>(iters, dc, ds);
+            if (mode == 6) k<0, 1><<<148, th>>>(iters, dc, ds);
+            if (mode == 7) k<0, 2><<<148, th>>>(iters, dc, ds);
             cudaDeviceSynchronize();
         }
         long long h[148]; cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost);
