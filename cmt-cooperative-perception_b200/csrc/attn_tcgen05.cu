@@ -24,6 +24,9 @@
 // Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
 // rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
 // than 2^8, so the common tile does no accumulator traffic at all.
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace cmt {
@@ -51,6 +54,9 @@ constexpr float RESCALE_THRESHOLD = 8.0f;
 #define CMT_ATTN_POLY_EVERY 0
 #endif
 constexpr int POLY_EVERY = CMT_ATTN_POLY_EVERY;
+#ifndef CMT_ATTN_ALU_PACK
+#define CMT_ATTN_ALU_PACK 0
+#endif
 }  // namespace attn
 
 // 2^x for x <= ~8 on the FMA/ALU pipes: split x = n + f, f in [-0.5, 0.5] with the 1.5*2^23 rounding trick,
@@ -71,18 +77,55 @@ struct TcAttnParams {
     int B, H, Nq;
     int kv_begin, kv_end;
     int T;            // KV tile-steps per item
-    int qblocks;      // ceil(Nq / 256)
+    int qblk;         // queries per item: 256 (two softmax warpgroups) or 384 (three)
+    int kt;           // KV tokens per tile-step: 128, or 64 for the double-buffered kernel
+    int qblocks;      // ceil(Nq / qblk)
     long long W;      // items * T
+    // Weighted stream-K: a step of an item whose last warpgroups are idle (the last query block of a frame/head
+    // when Nq is not a multiple of qblk) costs w_last instead of w_full; CTAs get equal WEIGHTED ranges.
+    int w_full, w_last;
+    long long Wg;     // weighted length of one (frame, head): T * (w_full * (qblocks - 1) + w_last)
+    long long Wtot;   // B * H * Wg
     int S_max;        // partial slots per item
-    float* part_o;    // [items*S_max][256][32]
-    float* part_lse;  // [items*S_max][256]   (log2 domain)
+    float* part_o;    // [items*S_max][qblk][32]
+    float* part_lse;  // [items*S_max][qblk]   (log2 domain)
+    long long* trace; // debug: clock64 event trace of CTA 0 (three-warpgroup kernel), nullptr = off
 };
+constexpr int TRACE_STEPS = 96;
+#define CMT_TRACE(wg_, step_, k_)                                                          \
+    do {                                                                                   \
+        if (p.trace != nullptr && blockIdx.x == 0 && (step_) < TRACE_STEPS)                \
+            p.trace[(static_cast<int>(wg_) * TRACE_STEPS + static_cast<int>(step_)) * 8 + (k_)] = clock64(); \
+    } while (0)
 
-__device__ __forceinline__ long long range_start(long long c, long long W, long long G) {
-    return (c * W) / G;
+// Weighted position of the start of global step x (x = item * T + step).
+__device__ __forceinline__ long long wpos_of(const TcAttnParams& p, long long x) {
+    const long long item = x / p.T;
+    const long long step = x - item * p.T;
+    const long long grp = item / p.qblocks;
+    const int qb = static_cast<int>(item - grp * p.qblocks);
+    return grp * p.Wg + static_cast<long long>(qb) * p.T * p.w_full + step * (qb == p.qblocks - 1 ? p.w_last : p.w_full);
 }
-__device__ __forceinline__ int cta_of(long long x, long long W, long long G) {
-    return static_cast<int>(((x + 1) * G + W - 1) / W - 1);
+// First global step of CTA c: the smallest x whose weighted position is >= c * Wtot / G.
+__device__ __forceinline__ long long range_start(const TcAttnParams& p, long long c, long long G) {
+    const long long t = (c * p.Wtot) / G;
+    const long long grp = t / p.Wg;
+    const long long rem = t - grp * p.Wg;
+    const long long full_span = static_cast<long long>(p.qblocks - 1) * p.T * p.w_full;
+    long long qb, step;
+    if (rem < full_span) {
+        qb = rem / (static_cast<long long>(p.T) * p.w_full);
+        step = (rem - qb * p.T * p.w_full + p.w_full - 1) / p.w_full;
+    } else {
+        qb = p.qblocks - 1;
+        step = (rem - full_span + p.w_last - 1) / p.w_last;
+    }
+    return (grp * p.qblocks + qb) * p.T + step;   // step == T carries into the next item
+}
+// The CTA whose range contains global step x.
+__device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long long G) {
+    const long long w = wpos_of(p, x);
+    return static_cast<int>(((w + 1) * G + p.Wtot - 1) / p.Wtot - 1);
 }
 
 __global__ void __launch_bounds__(attn::THREADS, 1)
@@ -103,7 +146,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     uint64_t* o_full = p_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see tc_attn_db_kernel)
+    const int lane = threadIdx.x & 31;
 
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tma_q);
@@ -126,16 +170,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const long long G = gridDim.x;
-    const long long pos_begin = range_start(blockIdx.x, p.W, G);
-    const long long pos_end = range_start(blockIdx.x + 1, p.W, G);
+    const long long pos_begin = range_start(p, blockIdx.x, G);
+    const long long pos_end = range_start(p, blockIdx.x + 1, G);
 
     if (warp >= 8) {
         setmaxnreg_dec<80>();
-        if (warp == 8 && lane == 0) {
+        if (warp == 8) {
             // ----------------------------- TMA producer -----------------------------
+            const bool leader = elect_one();
             uint32_t kc = 0, vc = 0, seg = 0;
             for (long long pos = pos_begin; pos < pos_end;) {
                 const int item = static_cast<int>(pos / p.T);
@@ -145,28 +190,35 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                 const int h = (item / p.qblocks) % p.H;
                 const int b = item / (p.qblocks * p.H);
                 mbar_wait(q_empty, (seg & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-                tma_load_4d(smem + OFF_Q, &tma_q, q_full, 0, qb * QBLK, h, b);
-                tma_load_4d(smem + OFF_Q + TILE_BYTES, &tma_q, q_full, 0, qb * QBLK + 128, h, b);
+                if (leader) {
+                    mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+                    tma_load_4d(smem + OFF_Q, &tma_q, q_full, 0, qb * QBLK, h, b);
+                    tma_load_4d(smem + OFF_Q + TILE_BYTES, &tma_q, q_full, 0, qb * QBLK + 128, h, b);
+                }
                 for (int jj = 0; jj < n; ++jj) {
                     const int tok0 = p.kv_begin + (j0 + jj) * KT;
                     const uint32_t ks = kc % NK, vs = vc % NV;
                     mbar_wait(&k_empty[ks], ((kc / NK) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-                    tma_load_4d(smem + OFF_K + ks * TILE_BYTES, &tma_k, &k_full[ks], 0, tok0, h, b);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+                        tma_load_4d(smem + OFF_K + ks * TILE_BYTES, &tma_k, &k_full[ks], 0, tok0, h, b);
+                    }
                     ++kc;
                     mbar_wait(&v_empty[vs], ((vc / NV) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-                    uint8_t* sv = smem + OFF_V + vs * TILE_BYTES;
-                    tma_load_4d(sv, &tma_v, &v_full[vs], tok0, 0, h, b);
-                    tma_load_4d(sv + TILE_BYTES / 2, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                        uint8_t* sv = smem + OFF_V + vs * TILE_BYTES;
+                        tma_load_4d(sv, &tma_v, &v_full[vs], tok0, 0, h, b);
+                        tma_load_4d(sv + TILE_BYTES / 2, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
+                    }
                     ++vc;
                 }
                 pos += n;
                 ++seg;
             }
-        } else if (warp == 9 && lane == 0) {
+        } else if (warp == 9) {
             // ------------------------------ MMA issuer ------------------------------
+            const bool leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
             const uint32_t sq = smem_u32(smem + OFF_Q);
@@ -182,16 +234,19 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                     mbar_wait(&k_full[ks], (kc / NK) & 1);
                     tc_fence_after();
                     const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
+                    if (leader) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
-                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
-                        tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
-                        tc_commit(&s_full[i]);
+                        for (int i = 0; i < 2; ++i) {
+                            const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                            tc_commit(&s_full[i]);
+                        }
+                        tc_commit(&k_empty[ks]);
+                        if (n == 1) tc_commit(q_empty);
                     }
-                    tc_commit(&k_empty[ks]);
+                    __syncwarp();
                     ++kc;
-                    if (n == 1) tc_commit(q_empty);
                 }
                 for (int jj = 0; jj < n; ++jj) {
                     const bool has_next = (jj + 1 < n);
@@ -207,28 +262,34 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                         mbar_wait(&p_full[i], p_cnt[i] & 1);
                         ++p_cnt[i];
                         tc_fence_after();
+                        if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint64_t vd = vdesc + (((kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32) >> 4);
-                            tc_mma_ts(tmem_base + COL_O + i * 32, tmem_base + COL_P + i * 64 + kk * 8, vd,
-                                      idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const uint64_t vd = vdesc + (((kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32) >> 4);
+                                tc_mma_ts(tmem_base + COL_O + i * 32, tmem_base + COL_P + i * 64 + kk * 8, vd,
+                                          idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
+                            }
+                            if (has_next) {
+                                const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
+                                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
+                                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
+                                tc_commit(&s_full[i]);
+                            } else {
+                                tc_commit(&o_full[i]);
+                            }
                         }
+                        __syncwarp();
+                    }
+                    if (leader) {
+                        tc_commit(&v_empty[vs]);
                         if (has_next) {
-                            const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
-                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
-                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
-                            tc_commit(&s_full[i]);
-                        } else {
-                            tc_commit(&o_full[i]);
+                            tc_commit(&k_empty[ks]);
+                            if (jj + 2 == n) tc_commit(q_empty);
                         }
                     }
-                    tc_commit(&v_empty[vs]);
+                    __syncwarp();
                     ++vc;
-                    if (has_next) {
-                        tc_commit(&k_empty[ks]);
-                        ++kc;
-                        if (jj + 2 == n) tc_commit(q_empty);
-                    }
+                    if (has_next) ++kc;
                 }
                 pos += n;
                 ++seg;
@@ -320,7 +381,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             uint32_t o[32];
             tmem_ld32(t_o, o);
             tc_wait_ld();
-            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(static_cast<long long>(item) * p.T, p.W, G));
+            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(p, static_cast<long long>(item) * p.T, G));
             const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
             const float inv = 1.0f / l;
             float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
@@ -343,31 +404,386 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Double-buffered-S variant ("db").  The traces of the kernels above (tools/attn_trace.py) show that what
+// keeps the MUFU pipe from saturating is the round trip P stored -> issuer wakes -> PV + next S MMA ->
+// softmax wakes (~900 cycles even with a back-to-back issuer) sitting inside every warpgroup's chain.
+// Here the KV tile is 64 tokens and every warpgroup owns TWO score buffers, so the scores of step j+1
+// (and j+2's, once PV(j) is issued) are already in TMEM while step j is being exponentiated: the
+// softmax warps never wait for the tensor pipe in steady state.
+//   TMEM: S_i,b at [128 i + 64 b, +64), P_i,b over the first 32 columns of S_i,b, O_i at [384 + 32 i, +32).
+//   barriers per warpgroup: s_full[b], p_full[b] (b = step & 1), pv_done (for the rare O rescale, which
+//   must not race the previous step's PV), o_full.
+//   512 threads: warps 0-11 softmax (one query row per thread, 64 scores in registers), 12 TMA + TMEM
+//   allocation, 13-15 one MMA issuer per warpgroup.  No setmaxnreg: 128 registers per thread are enough
+//   for 64-column tiles.
+namespace attndb {
+#ifndef CMT_ATTN_NWG
+#define CMT_ATTN_NWG 3
+#endif
+constexpr int NWG = CMT_ATTN_NWG;
+constexpr int QBLK = NWG * 128;
+constexpr int KT = 64;
+constexpr int NK = 8, NV = 8;
+constexpr int Q_BYTES = 128 * 32 * 2;   // 8 KB per Q tile
+constexpr int KV_BYTES = 64 * 32 * 2;   // 4 KB per K tile / V^T tile
+#ifndef CMT_ATTN_NISS
+#define CMT_ATTN_NISS 1
+#endif
+#ifndef CMT_ISSUER_WAIT
+#define CMT_ISSUER_WAIT mbar_wait
+#endif
+constexpr int NISS = CMT_ATTN_NISS;                    // MMA issuer warps (warpgroup i is served by issuer i % NISS)
+constexpr int THREADS = NWG * 128 + 32 + NISS * 32;   // softmax warps, TMA warp, issuer warps
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + NWG * Q_BYTES;
+constexpr int OFF_V = OFF_K + NK * KV_BYTES;
+constexpr int OFF_BAR = OFF_V + NV * KV_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr uint32_t COL_O = 384;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+}  // namespace attndb
+
+__global__ void __launch_bounds__(attndb::THREADS, 1)
+tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
+    using namespace attndb;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* k_full = bars + 2;             // [NK]
+    uint64_t* k_empty = k_full + NK;         // [NK]
+    uint64_t* v_full = k_empty + NK;         // [NV]
+    uint64_t* v_empty = v_full + NV;         // [NV]
+    uint64_t* s_full = v_empty + NV;         // [NWG][2]
+    uint64_t* p_full = s_full + 2 * NWG;     // [NWG][2]
+    uint64_t* pv_done = p_full + 2 * NWG;    // [NWG]
+    uint64_t* o_full = pv_done + NWG;        // [NWG]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NWG);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
+    constexpr int W_TMA = NWG * 4, W_MMA = NWG * 4 + 1;   // issuers: W_MMA .. W_MMA + NWG - 1
+
+    if (warp == W_MMA && lane == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_v);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, NISS);   // every issuer releases the Q / K / V stages
+        for (int s = 0; s < NK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], NISS); }
+        for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], NISS); }
+        for (int i = 0; i < NWG; ++i) {
+            mbar_init(&s_full[2 * i], 1);
+            mbar_init(&s_full[2 * i + 1], 1);
+            mbar_init(&p_full[2 * i], 128);
+            mbar_init(&p_full[2 * i + 1], 128);
+            mbar_init(&pv_done[i], 1);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const long long t_start = clock64();
+    const long long G = gridDim.x;
+    const long long pos_begin = range_start(p, blockIdx.x, G);
+    const long long pos_end = range_start(p, blockIdx.x + 1, G);
+
+    if (warp == W_TMA) {
+        // ----------------------------- TMA producer -----------------------------
+        const bool leader = elect_one();
+        uint32_t kc = 0, vc = 0, seg = 0;
+        for (long long pos = pos_begin; pos < pos_end;) {
+            const int item = static_cast<int>(pos / p.T);
+            const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+            const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            const int qb = item % p.qblocks;
+            const int h = (item / p.qblocks) % p.H;
+            const int b = item / (p.qblocks * p.H);
+            int nact = (p.Nq - qb * QBLK + 127) >> 7;
+            nact = nact > NWG ? NWG : nact;
+            mbar_wait_sleep(q_empty, (seg & 1) ^ 1);
+            if (leader) {
+                mbar_arrive_expect_tx(q_full, nact * Q_BYTES);
+                for (int i = 0; i < nact; ++i)
+                    tma_load_4d(smem + OFF_Q + i * Q_BYTES, &tma_q, q_full, 0, qb * QBLK + i * 128, h, b);
+            }
+            // K runs two steps ahead of V: the issuer needs K(j+2) when it retires step j
+            const int tok_base = p.kv_begin + j0 * KT;
+            for (int jj = 0; jj < n + 2; ++jj) {
+                if (jj < n) {
+                    const uint32_t ks = kc % NK;
+                    mbar_wait_sleep(&k_empty[ks], ((kc / NK) & 1) ^ 1);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&k_full[ks], KV_BYTES);
+                        tma_load_4d(smem + OFF_K + ks * KV_BYTES, &tma_k, &k_full[ks], 0, tok_base + jj * KT, h, b);
+                    }
+                    ++kc;
+                }
+                if (jj >= 2) {
+                    const uint32_t vs = vc % NV;
+                    mbar_wait_sleep(&v_empty[vs], ((vc / NV) & 1) ^ 1);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&v_full[vs], KV_BYTES);
+                        tma_load_4d(smem + OFF_V + vs * KV_BYTES, &tma_v, &v_full[vs], tok_base + (jj - 2) * KT, 0, h, b);
+                    }
+                    ++vc;
+                }
+            }
+            pos += n;
+            ++seg;
+        }
+    } else if (warp >= W_MMA) {
+        // ------------- MMA issuers: warp W_MMA + ii serves the warpgroups i with i % NISS == ii -------------
+        const int ii = warp - W_MMA;
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
+        const uint32_t sq = smem_u32(smem + OFF_Q);
+        uint32_t kc = 0, vc = 0, seg = 0;
+        uint32_t g[NWG];                       // steps retired per warpgroup (buffer = g & 1, parity = (g >> 1) & 1)
+#pragma unroll
+        for (int i = 0; i < NWG; ++i) g[i] = 0;
+        for (long long pos = pos_begin; pos < pos_end;) {
+            const int item = static_cast<int>(pos / p.T);
+            const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+            const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            const int qb = item % p.qblocks;
+            int nact = (p.Nq - qb * QBLK + 127) >> 7;   // warpgroups with queries; the others only release stages
+            nact = nact > NWG ? NWG : nact;
+            mbar_wait_sleep(q_full, seg & 1);
+            // prologue: scores of steps 0 and 1 into the two buffers
+            for (int pre = 0; pre < 2 && pre < n; ++pre) {
+                const uint32_t ks = kc % NK;
+                mbar_wait_sleep(&k_full[ks], (kc / NK) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * KV_BYTES), 64);
+#pragma unroll
+                    for (int i = 0; i < NWG; ++i) {
+                        if ((i % NISS) == ii && i < nact) {
+                            const uint32_t bsel = (g[i] + pre) & 1;
+                            const uint64_t qdesc = make_kmajor_desc(sq + i * Q_BYTES, 64);
+                            tc_mma_ss(tmem_base + i * 128 + bsel * 64, qdesc, kdesc, idesc_s, 0);
+                            tc_mma_ss(tmem_base + i * 128 + bsel * 64, qdesc + 2, kdesc + 2, idesc_s, 1);
+                            tc_commit(&s_full[2 * i + bsel]);
+                        }
+                    }
+                    tc_commit(&k_empty[ks]);
+                    if (pre + 1 == n) tc_commit(q_empty);
+                }
+                __syncwarp();
+                ++kc;
+            }
+            for (int jj = 0; jj < n; ++jj) {
+                const bool has2 = (jj + 2 < n);
+                const uint32_t vs = vc % NV;
+                const uint32_t ks = kc % NK;
+                mbar_wait_sleep(&v_full[vs], (vc / NV) & 1);
+                if (has2) mbar_wait_sleep(&k_full[ks], (kc / NK) & 1);
+                const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * KV_BYTES), 128);
+                const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * KV_BYTES), 64);
+#pragma unroll
+                for (int i = 0; i < NWG; ++i) {
+                    if ((i % NISS) == ii && i < nact) {
+                        const uint32_t bsel = g[i] & 1;
+                        CMT_ISSUER_WAIT(&p_full[2 * i + bsel], (g[i] >> 1) & 1);
+                        tc_fence_after();
+                        if (leader) {
+                            CMT_TRACE(i, g[i], 4);
+                            const uint32_t t_sp = tmem_base + i * 128 + bsel * 64;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_ts(tmem_base + COL_O + i * 32, t_sp + kk * 8, vdesc + ((kk * 32) >> 4), idesc_o,
+                                          (jj > 0 || kk > 0) ? 1u : 0u);
+                            if (jj + 1 == n) tc_commit(&o_full[i]);
+                            else tc_commit(&pv_done[i]);
+                            if (has2) {
+                                const uint64_t qdesc = make_kmajor_desc(sq + i * Q_BYTES, 64);
+                                tc_mma_ss(t_sp, qdesc, kdesc, idesc_s, 0);
+                                tc_mma_ss(t_sp, qdesc + 2, kdesc + 2, idesc_s, 1);
+                                tc_commit(&s_full[2 * i + bsel]);
+                            }
+                            CMT_TRACE(i, g[i], 5);
+                        }
+                        __syncwarp();
+                        ++g[i];
+                    }
+                }
+                if (leader) {
+                    tc_commit(&v_empty[vs]);
+                    if (has2) {
+                        tc_commit(&k_empty[ks]);
+                        if (jj + 3 == n) tc_commit(q_empty);
+                    }
+                }
+                __syncwarp();
+                ++vc;
+                if (has2) ++kc;
+            }
+            pos += n;
+            ++seg;
+        }
+    } else {
+        // --------------------------- softmax warpgroups ---------------------------
+        const int wg = warp >> 2;                       // Q tile of the item
+        const int r = (warp & 3) * 32 + lane;           // row inside the 128-row tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_base + wg * 128;   // + 64 * buffer
+        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
+        uint64_t* my_s_full = s_full + 2 * wg;
+        uint64_t* my_p_full = p_full + 2 * wg;
+        const bool tracer = (threadIdx.x & 127) == 0;
+        uint32_t g = 0, seg = 0, pv_base = 0;   // pv_base: pv_done phases of the earlier segments (n - 1 each)
+        for (long long pos = pos_begin; pos < pos_end;) {
+            const int item = static_cast<int>(pos / p.T);
+            const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
+            const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            const int qb = item % p.qblocks;
+            pos += n;
+            if (qb * QBLK + wg * 128 >= p.Nq) continue;     // this warpgroup's tile is past the last query
+            float m = -INFINITY, l = 0.0f;
+            for (int jj = 0; jj < n; ++jj, ++g) {
+                const uint32_t bsel = g & 1;
+                const uint32_t t_sb = t_s + bsel * 64;
+                mbar_wait(&my_s_full[bsel], (g >> 1) & 1);
+                if (tracer) CMT_TRACE(wg, g, 0);
+                tc_fence_after();
+                uint32_t s[2][32];
+                tmem_ld32(t_sb + 0, s[0]);
+                tmem_ld32(t_sb + 32, s[1]);
+                tc_wait_ld();
+                if (tracer) CMT_TRACE(wg, g, 1);
+                const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
+                if (valid < KT) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[0][16 + i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[1][i]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[1][16 + i]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (jj == 0) {
+                    m = mx;  // O_i is overwritten by the first PV of the segment: nothing to rescale
+                } else {
+                    const bool need = (mx - m) > RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // PV(step - 1) may still be accumulating into O_i: wait for it before touching O_i
+                        mbar_wait(&pv_done[wg], (pv_base + jj - 1) & 1);
+                        tc_fence_after();
+                        const float m_new = need ? mx : m;
+                        const float alpha = ex2_approx(m - m_new);
+                        l *= alpha;
+                        uint32_t o[32];
+                        tmem_ld32(t_o, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_o, o);
+                        m = m_new;
+                    }
+                }
+                if (tracer) CMT_TRACE(wg, g, 2);
+                // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs
+                const uint64_t neg_m2 = pack_f32x2(-m, -m);
+                uint64_t l2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x0, x1;
+                        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2), x0, x1);
+                        const float e0 = ex2_approx(x0);
+                        // one exponential in 2 * POLY_EVERY can run on the FMA/ALU pipes instead of the MUFU (0 = off)
+                        const float e1 = (attn::POLY_EVERY > 0 && (i % (attn::POLY_EVERY > 0 ? attn::POLY_EVERY : 1)) == attn::POLY_EVERY - 1)
+                                             ? ex2_poly(x1) : ex2_approx(x1);
+                        l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                        pk[i] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st16(t_sb + c * 16, pk);
+                }
+                {
+                    float l0, l1;
+                    unpack_f32x2(l2, l0, l1);
+                    l += l0 + l1;
+                }
+                tc_wait_st();
+                if (tracer) CMT_TRACE(wg, g, 3);
+                tc_fence_before();
+                mbar_arrive(&my_p_full[bsel]);
+            }
+            // segment epilogue: normalised partial + log2-sum-exp into the workspace
+            mbar_wait(&o_full[wg], seg & 1);
+            ++seg;
+            pv_base += n - 1;
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld32(t_o, o);
+            tc_wait_ld();
+            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(p, static_cast<long long>(item) * p.T, G));
+            const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
+            const float inv = 1.0f / l;
+            float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
+                                     __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
+            p.part_lse[prow] = m + log2f(l);
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[3 * TRACE_STEPS * 8 + blockIdx.x] = clock64() - t_start;
+    if (warp == W_TMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Merge the per-CTA segments of each item.  One thread = (item row, 4 output dims).
 template <bool kBf16>
 __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long long G, void* o,
                                                             float* lse) {
     const long long items = static_cast<long long>(p.B) * p.H * p.qblocks;
-    const long long total = items * attn::QBLK * 8;
+    const int QB = p.qblk;
+    const long long total = items * QB * 8;
     for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int q4 = static_cast<int>(t & 7);
-        const int rr = static_cast<int>((t >> 3) % attn::QBLK);
-        const int item = static_cast<int>((t >> 3) / attn::QBLK);
+        const int rr = static_cast<int>((t >> 3) % QB);
+        const int item = static_cast<int>((t >> 3) / QB);
         const int qb = item % p.qblocks;
         const int h = (item / p.qblocks) % p.H;
         const int b = item / (p.qblocks * p.H);
-        const int row = qb * attn::QBLK + rr;
+        const int row = qb * QB + rr;
         if (row >= p.Nq) continue;
         const long long x0 = static_cast<long long>(item) * p.T;
-        const int nseg = cta_of(x0 + p.T - 1, p.W, G) - cta_of(x0, p.W, G) + 1;
+        const int nseg = cta_of(p, x0 + p.T - 1, G) - cta_of(p, x0, G) + 1;
         float mx = -INFINITY;
         for (int s = 0; s < nseg; ++s)
-            mx = fmaxf(mx, p.part_lse[(static_cast<long long>(item) * p.S_max + s) * attn::QBLK + rr]);
+            mx = fmaxf(mx, p.part_lse[(static_cast<long long>(item) * p.S_max + s) * QB + rr]);
         float den = 0.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < nseg; ++s) {
-            const long long prow = (static_cast<long long>(item) * p.S_max + s) * attn::QBLK + rr;
+            const long long prow = (static_cast<long long>(item) * p.S_max + s) * QB + rr;
             const float w = exp2f(p.part_lse[prow] - mx);
             den += w;
             const float4 x = reinterpret_cast<const float4*>(p.part_o + prow * 32)[q4];
@@ -392,20 +808,50 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
     }
 }
 
+// Kernel variant, read once per process from CMT_ATTN_VARIANT: "db" (default: three warpgroups, double-buffered
+// scores, 64-token tiles) or "wg2" (the first schedule: two warpgroups, 128-token tiles, single score buffer).
+enum AttnVariant { kAttnDb = 0, kAttnWg2 = 2 };
+static AttnVariant attn_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CMT_ATTN_VARIANT");
+        v = kAttnDb;
+        if (e != nullptr && strcmp(e, "wg2") == 0) v = kAttnWg2;
+    }
+    return static_cast<AttnVariant>(v);
+}
+
 static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid) {
-    p->qblocks = (Nq + attn::QBLK - 1) / attn::QBLK;
-    p->T = (n_tok + attn::KT - 1) / attn::KT;
+    const AttnVariant var = attn_variant();
+    p->qblk = var == kAttnWg2 ? attn::QBLK : attndb::QBLK;
+    p->kt = var == kAttnDb ? attndb::KT : attn::KT;
+    p->qblocks = (Nq + p->qblk - 1) / p->qblk;
+    p->T = (n_tok + p->kt - 1) / p->kt;
     const long long items = static_cast<long long>(B) * H * p->qblocks;
     p->W = items * p->T;
+    // step weights (measured, tools/attn_trace.py): with every warpgroup active a step is MUFU-bound; with an
+    // idle warpgroup it is bound by one warpgroup's own chain, ~3/4 of that
+    p->w_full = 4;
+    p->w_last = 4;
+    if (var == kAttnDb) {
+        const int nact_last = (Nq - (p->qblocks - 1) * p->qblk + 127) / 128;
+        if (nact_last < attndb::NWG) p->w_last = 3;
+    }
+    p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
+    p->Wtot = static_cast<long long>(B) * H * p->Wg;
+    // every CTA must own at least one step: weighted ranges no shorter than the widest step
     long long G = sms;
-    if (G > p->W) G = p->W;
+    if (G > p->Wtot / p->w_full) G = p->Wtot / p->w_full;
     if (G < 1) G = 1;
-    const long long chunk_min = p->W / G;  // >= 1
-    p->S_max = static_cast<int>((p->T - 1) / chunk_min + 2);
+    const long long chunk_min = p->Wtot / G;  // >= w_full
+    p->S_max = static_cast<int>((static_cast<long long>(p->T) * p->w_full - 1) / chunk_min + 2);
     *grid = static_cast<int>(G);
 }
 
-int tc_attn_set_timing_buffer(long long*) { return CMT_OK; }  // phase-timing hook of the experimental builds (unused)
+// Debug hook: device buffer of 3 * TRACE_STEPS * 8 int64 that CTA 0 of the three-warpgroup kernel fills with
+// clock64 stamps (tools/attn_trace.py).  nullptr switches the trace off.
+static long long* g_trace_buf = nullptr;
+int tc_attn_set_timing_buffer(long long* dev_buf) { g_trace_buf = dev_buf; return CMT_OK; }
 
 size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
@@ -413,7 +859,7 @@ size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     int grid;
     attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid);
     const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
-    return slots * attn::QBLK * 33 * sizeof(float) + 256;
+    return slots * p.qblk * 33 * sizeof(float) + 256;
 }
 
 int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -442,12 +888,15 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     const size_t slots = static_cast<size_t>(a.B) * a.H * p.qblocks * p.S_max;
     uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     p.part_o = reinterpret_cast<float*>(wsp);
-    p.part_lse = p.part_o + slots * QBLK * 32;
+    p.part_lse = p.part_o + slots * p.qblk * 32;
+    p.trace = g_trace_buf;
 
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn)");
+        e = cudaFuncSetAttribute(tc_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
         attr_done = true;
     }
     CUtensorMap tq, tk, tv;
@@ -461,7 +910,7 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     {
         uint64_t dims[4] = {32, static_cast<uint64_t>(a.kv_end), static_cast<uint64_t>(a.H), static_cast<uint64_t>(a.B)};
         uint64_t strides[3] = {64, static_cast<uint64_t>(a.k_hstride) * 2, static_cast<uint64_t>(a.k_bstride) * 2};
-        uint32_t box[4] = {32, KT, 1, 1};
+        uint32_t box[4] = {32, static_cast<uint32_t>(p.kt), 1, 1};
         int rc = encode_tma_bf16(&tk, a.k, 4, dims, strides, box, 64);
         if (rc) return rc;
     }
@@ -473,9 +922,12 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
         int rc = encode_tma_bf16(&tv, a.vt, 4, dims, strides, box, 128);
         if (rc) return rc;
     }
-    tc_attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    if (attn_variant() == kAttnDb)
+        tc_attn_db_kernel<<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    else
+        tc_attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
-    const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * QBLK * 8;
+    const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * p.qblk * 8;
     long long mblocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(device_sm_count()) * 8;
     if (mblocks > cap) mblocks = cap;

@@ -9,10 +9,20 @@
 #include "../../cmt-cooperative-perception_b200/csrc/common.cuh"
 namespace cmt { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return -2; } }
 using namespace cmt;
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;
+    const float n = t - 12582912.0f;
+    const float f = x - n;
+    float p = fmaf(f, 0.0555054f, 0.2402265f);
+    p = fmaf(p, f, 0.6931472f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
-template <int MODE, int PACK = 0>  // PACK 0: cvt.rn.bf16x2 (F2FP); 1: integer round + PRMT; 2: PRMT truncate
+template <int MODE, int PACK = 0, int POLY = 0>  // POLY n>0: one exponential in 2n on the FMA pipes (cubic)  // PACK 0: cvt.rn.bf16x2 (F2FP); 1: integer round + PRMT; 2: PRMT truncate
 // MODE 0: full; 1: no TMEM ld/st (registers only); 2: no exps (ld/max/st only); 3: chunked (max from previous tile)
-__global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32_t* sink) {
+__global__ void __launch_bounds__(384, 1) k(int iters, long long* cycles, uint32_t* sink) {
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
     if (warp == 0) tmem_alloc(&slot, 512);
@@ -50,7 +60,7 @@ __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, uint32
             for (int i = 0; i < 16; ++i) {
                 float e0, e1;
                 if (MODE == 2) { e0 = __uint_as_float(s[c][2 * i]) - m; e1 = __uint_as_float(s[c][2 * i + 1]) - m; }
-                else { e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m); e1 = ex2_approx(__uint_as_float(s[c][2 * i + 1]) - m); }
+                else { e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m); const float x1 = __uint_as_float(s[c][2 * i + 1]) - m; e1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1); }
                 if (PACK == 0) pk[i] = pack_bf16x2(e0, e1);
                 else if (PACK == 1) pk[i] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
                 else pk[i] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
@@ -74,7 +84,7 @@ int main() {
     long long* dc; uint32_t* ds; cudaMalloc(&dc, 148 * 8); cudaMalloc(&ds, 4);
     const int iters = 2000;
     const char* names[8] = {"full (ld, max, exp, pack, st)", "registers only (no TMEM)", "no exp (ld, max, pack, st)", "full, stale max",
-                            "registers only, round+PRMT pack", "registers only, PRMT truncate", "full, round+PRMT pack", "full, PRMT truncate"};
+                            "full, poly 1/2", "full, poly 1/4", "full, poly 1/8", "full, poly 1/16"};
     for (int mode = 0; mode < 8; ++mode) {
         for (int rep = 0; rep < 2; ++rep) {
             const int th = getenv("THREADS") ? atoi(getenv("THREADS")) : 256;
@@ -82,10 +92,10 @@ int main() {
             if (mode == 1) k<1><<<148, th>>>(iters, dc, ds);
             if (mode == 2) k<2><<<148, th>>>(iters, dc, ds);
             if (mode == 3) k<3><<<148, th>>>(iters, dc, ds);
-            if (mode == 4) k<1, 1><<<148, th>>>(iters, dc, ds);
-            if (mode == 5) k<1, 2><<<148, th>>>(iters, dc, ds);
-            if (mode == 6) k<0, 1><<<148, th>>>(iters, dc, ds);
-            if (mode == 7) k<0, 2><<<148, th>>>(iters, dc, ds);
+            if (mode == 4) k<0, 0, 1><<<148, th>>>(iters, dc, ds);
+            if (mode == 5) k<0, 0, 2><<<148, th>>>(iters, dc, ds);
+            if (mode == 6) k<0, 0, 4><<<148, th>>>(iters, dc, ds);
+            if (mode == 7) k<0, 0, 8><<<148, th>>>(iters, dc, ds);
             cudaDeviceSynchronize();
         }
         long long h[148]; cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost);
