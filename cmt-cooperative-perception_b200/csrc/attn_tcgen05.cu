@@ -60,17 +60,39 @@ constexpr int POLY_EVERY = CMT_ATTN_POLY_EVERY;
 }  // namespace attn
 
 // 2^x for x <= ~8 on the FMA/ALU pipes: split x = n + f, f in [-0.5, 0.5] with the 1.5*2^23 rounding trick,
-// 2^f by a cubic (relative error < 7e-4, below the 2^-9 rounding P gets anyway), 2^n by adding n to the
+// 2^f by the minimax cubic (relative error 7.5e-5, far below the 2^-9 rounding P gets anyway), 2^n by adding n to the
 // exponent field.  Inputs below -125 (masked scores are -inf) clamp to 2^-125, i.e. nothing after rounding.
 __device__ __forceinline__ float ex2_poly(float x) {
     x = fmaxf(x, -125.0f);
     const float t = x + 12582912.0f;
     const float n = t - 12582912.0f;
     const float f = x - n;
-    float p = fmaf(f, 0.0555054f, 0.2402265f);
-    p = fmaf(p, f, 0.6931472f);
-    p = fmaf(p, f, 1.0f);
+    float p = fmaf(f, 0.05517167f, 0.24261113f);   // minimax cubic of 2^f on [-0.5, 0.5]: 7.5e-5 relative
+    p = fmaf(p, f, 0.69326097f);
+    p = fmaf(p, f, 0.99992806f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// The same cubic on a PAIR of inputs with the packed fp32 instructions (FADD2 / FFMA2): 2 clamps, 3 FADD2,
+// 3 FFMA2 and 2 integer ops for two exponentials, i.e. ~5 issue slots per exponential and no MUFU slot.
+__device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x2 = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+    const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+    const uint64_t m1 = pack_f32x2(-1.0f, -1.0f);
+    const uint64_t t2 = add_f32x2(x2, magic);
+    const uint64_t n2 = add_f32x2(t2, nmagic);
+    const uint64_t f2 = fma_f32x2(n2, m1, x2);   // x - n
+    uint64_t p2 = fma_f32x2(f2, pack_f32x2(0.05517167f, 0.05517167f), pack_f32x2(0.24261113f, 0.24261113f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.69326097f, 0.69326097f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.99992806f, 0.99992806f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 struct TcAttnParams {
@@ -442,6 +464,14 @@ constexpr int OFF_BAR = OFF_V + NV * KV_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr uint32_t COL_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;
+// With the scores double-buffered and the packed FADD2 softmax, the steady-state step sits within ~7 % of the
+// MUFU bound (16 ex2 / clk / SM), so moving exponentials to the FMA pipes pays: pairs i with i % DB_POLY ==
+// DB_POLY - 1 of every 16-pair chunk use the packed cubic (ex2_poly_pair).  Measured (B=8, 56 400 tokens, same
+// box): off 1100 us, 1/16 1110, 1/8 1056, 1/6 1029, 1/5 1077, 1/4 1106, 1/3 1140, 1/2 1190.
+#ifndef CMT_ATTN_DB_POLY
+#define CMT_ATTN_DB_POLY 6
+#endif
+constexpr int DB_POLY = CMT_ATTN_DB_POLY;
 }  // namespace attndb
 
 __global__ void __launch_bounds__(attndb::THREADS, 1)
@@ -707,12 +737,17 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float x0, x1;
-                        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2), x0, x1);
-                        const float e0 = ex2_approx(x0);
-                        // one exponential in 2 * POLY_EVERY can run on the FMA/ALU pipes instead of the MUFU (0 = off)
-                        const float e1 = (attn::POLY_EVERY > 0 && (i % (attn::POLY_EVERY > 0 ? attn::POLY_EVERY : 1)) == attn::POLY_EVERY - 1)
-                                             ? ex2_poly(x1) : ex2_approx(x1);
+                        const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
+                        float e0, e1;
+                        // one PAIR of exponentials in DB_POLY runs on the FMA pipes (packed cubic) instead of the MUFU
+                        if (DB_POLY > 0 && (i % (DB_POLY > 0 ? DB_POLY : 1)) == DB_POLY - 1) {
+                            ex2_poly_pair(x2, e0, e1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
                         l2 = add_f32x2(l2, pack_f32x2(e0, e1));
                         pk[i] = pack_bf16x2(e0, e1);
                     }

@@ -55,7 +55,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index / TMEM base through shuffles: provably warp-uniform, so the producer and issuer warps keep
+    // their descriptors in uniform registers and TMA / tcgen05.mma instructions issue back to back (a divergent
+    // `lane == 0` role costs a ~12-instruction ELECT/R2UR waterfall per instruction).
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -76,13 +80,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int tiles_per_batch = p.m_tiles * p.n_tiles;
 
     if (warp == 0) {
         // ----------------------------- TMA producer -----------------------------
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -91,18 +96,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
-                    tma_load_3d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                    if (leader) {
+                        uint8_t* sa = smem + stage * STAGE_BYTES;
+                        uint8_t* sb = sa + A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
+                        tma_load_3d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -115,18 +124,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_desc(sa, 128);
-                    const uint64_t bdesc = make_kmajor_desc(sa + A_BYTES, 128);
+                    if (leader) {
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_desc(sa, 128);
+                        const uint64_t bdesc = make_kmajor_desc(sa + A_BYTES, 128);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 bytes per K=16 step inside the 128B swizzle atom (>>4 -> +2)
-                        tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 bytes per K=16 step inside the 128B swizzle atom (>>4 -> +2)
+                            tc_mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                     }
-                    tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tmem_full[acc]);
+                if (leader) tc_commit(&tmem_full[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
