@@ -114,11 +114,15 @@ struct TcAttnParams {
     long long* trace; // debug: clock64 event trace of CTA 0 (three-warpgroup kernel), nullptr = off
 };
 constexpr int TRACE_STEPS = 96;
+#ifdef CMT_ATTN_TRACE
 #define CMT_TRACE(wg_, step_, k_)                                                          \
     do {                                                                                   \
         if (p.trace != nullptr && blockIdx.x == 0 && (step_) < TRACE_STEPS)                \
-            p.trace[(static_cast<int>(wg_) * TRACE_STEPS + static_cast<int>(step_)) * 8 + (k_)] = clock64(); \
+            p.trace[(static_cast<int>(wg_) * TRACE_STEPS + static_cast<int>(step_)) * 16 + (k_)] = clock64(); \
     } while (0)
+#else
+#define CMT_TRACE(wg_, step_, k_) do { } while (0)
+#endif
 
 // Weighted position of the start of global step x (x = item * T + step).
 __device__ __forceinline__ long long wpos_of(const TcAttnParams& p, long long x) {
@@ -449,11 +453,29 @@ constexpr int KT = 64;
 constexpr int NK = 8, NV = 8;
 constexpr int Q_BYTES = 128 * 32 * 2;   // 8 KB per Q tile
 constexpr int KV_BYTES = 64 * 32 * 2;   // 4 KB per K tile / V^T tile
+// MMA issuer warps.  tools/attn_trace.py (per-warp stamps) shows that the softmax warps which share an SM
+// sub-partition with an issuer warp take longer per step than the others, and that the slowest warp of a
+// warpgroup sets the period (P needs all four warps).  One issuer per warpgroup spreads that cost over three
+// sub-partitions, and the issuers sleep in hardware on their P waits (try_wait with a suspend hint) instead of
+// polling: their wake-up latency hides under the double-buffered scores, their issue slots do not.
+// Measured (B=8, 56 400 tokens, us per launch): 1 polling issuer 1058, 1 sleeping 1056, 3 polling 992, 3 sleeping 983.
 #ifndef CMT_ATTN_NISS
-#define CMT_ATTN_NISS 1
+#define CMT_ATTN_NISS 3
 #endif
 #ifndef CMT_ISSUER_WAIT
-#define CMT_ISSUER_WAIT mbar_wait
+#define CMT_ISSUER_WAIT mbar_wait_sleep
+#endif
+#ifndef CMT_TOK_WAIT
+#define CMT_TOK_WAIT mbar_wait_sleep      // softmax warps: MUFU token
+#endif
+#ifndef CMT_S_WAIT
+#define CMT_S_WAIT mbar_wait              // softmax warps: scores ready
+#endif
+#ifndef CMT_KV_WAIT
+#define CMT_KV_WAIT mbar_wait_sleep       // issuer: K / V stage full
+#endif
+#ifndef CMT_PROD_WAIT
+#define CMT_PROD_WAIT mbar_wait_sleep     // TMA producer: K / V stage empty
 #endif
 constexpr int NISS = CMT_ATTN_NISS;                    // MMA issuer warps (warpgroup i is served by issuer i % NISS)
 constexpr int THREADS = NWG * 128 + 32 + NISS * 32;   // softmax warps, TMA warp, issuer warps
@@ -461,7 +483,7 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + NWG * Q_BYTES;
 constexpr int OFF_V = OFF_K + NK * KV_BYTES;
 constexpr int OFF_BAR = OFF_V + NV * KV_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
 constexpr uint32_t COL_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 // With the scores double-buffered and the packed FADD2 softmax, the steady-state step sits within ~7 % of the
@@ -472,6 +494,24 @@ constexpr float RESCALE_THRESHOLD = 8.0f;
 #define CMT_ATTN_DB_POLY 6
 #endif
 constexpr int DB_POLY = CMT_ATTN_DB_POLY;
+// MUFU token ring.  The three softmax warps that share an SM sub-partition (warp w of every warpgroup) contend for
+// its 4-lane MUFU pipe; left alone they fall into a convoy: all three exponentiate together at a third of the rate,
+// finish together, and then all three sit in their MUFU-free phases (TMEM load, row max, P store, barrier round
+// trips) with the pipe idle.  A token per sub-partition serialises the exponential phases instead: warpgroup i
+// waits for its token, exponentiates at full rate and hands the token to warpgroup i+1 after RING_REL of its 32
+// pairs, so the successor's wake-up overlaps the tail and the other two warps' MUFU-free phases hide under it.
+// No token is ever held across a blocking wait, idle warpgroups / all-padding warps just pass it on.
+// Measured: 1058 -> 1015 us with one polling issuer, 992 -> 979 with three, 983 -> 986 with three sleeping issuers
+// (the shipped configuration): the convoy is not what limits the kernel once the issuers are out of the way, and the
+// SM clock under this kernel is ~1.6 GHz (power), so a step is already within ~10 % of the MUFU floor.  Off by default.
+#ifndef CMT_ATTN_RING
+#define CMT_ATTN_RING 0
+#endif
+#ifndef CMT_ATTN_RING_REL
+#define CMT_ATTN_RING_REL 22
+#endif
+constexpr bool RING = CMT_ATTN_RING != 0;
+constexpr int RING_REL = CMT_ATTN_RING_REL;
 }  // namespace attndb
 
 __global__ void __launch_bounds__(attndb::THREADS, 1)
@@ -491,11 +531,16 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     uint64_t* p_full = s_full + 2 * NWG;     // [NWG][2]
     uint64_t* pv_done = p_full + 2 * NWG;    // [NWG]
     uint64_t* o_full = pv_done + NWG;        // [NWG]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NWG);
+    uint64_t* tok = o_full + NWG;            // [NWG][4] MUFU tokens: (warpgroup, warp of the warpgroup)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 4 * NWG);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
-    constexpr int W_TMA = NWG * 4, W_MMA = NWG * 4 + 1;   // issuers: W_MMA .. W_MMA + NWG - 1
+#ifdef CMT_ATTN_TMA_LAST
+    constexpr int W_MMA = NWG * 4, W_TMA = NWG * 4 + NISS;   // issuers: W_MMA .. W_MMA + NISS - 1
+#else
+    constexpr int W_TMA = NWG * 4, W_MMA = NWG * 4 + 1;   // issuers: W_MMA .. W_MMA + NISS - 1
+#endif
 
     if (warp == W_MMA && lane == 0) {
         tma_prefetch_desc(&tma_q);
@@ -513,7 +558,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             mbar_init(&pv_done[i], 1);
             mbar_init(&o_full[i], 1);
         }
+        for (int i = 0; i < 4 * NWG; ++i) mbar_init(&tok[i], 1);
         fence_barrier_init();
+        for (int w = 0; w < 4; ++w) mbar_arrive(&tok[w]);   // warpgroup 0 owns the tokens first
     }
     if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -521,7 +568,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    const long long t_start = clock64();
+    const long long t_start = p.trace != nullptr ? clock64() : 0;
     const long long G = gridDim.x;
     const long long pos_begin = range_start(p, blockIdx.x, G);
     const long long pos_end = range_start(p, blockIdx.x + 1, G);
@@ -550,7 +597,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             for (int jj = 0; jj < n + 2; ++jj) {
                 if (jj < n) {
                     const uint32_t ks = kc % NK;
-                    mbar_wait_sleep(&k_empty[ks], ((kc / NK) & 1) ^ 1);
+                    CMT_PROD_WAIT(&k_empty[ks], ((kc / NK) & 1) ^ 1);
                     if (leader) {
                         mbar_arrive_expect_tx(&k_full[ks], KV_BYTES);
                         tma_load_4d(smem + OFF_K + ks * KV_BYTES, &tma_k, &k_full[ks], 0, tok_base + jj * KT, h, b);
@@ -559,7 +606,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 }
                 if (jj >= 2) {
                     const uint32_t vs = vc % NV;
-                    mbar_wait_sleep(&v_empty[vs], ((vc / NV) & 1) ^ 1);
+                    CMT_PROD_WAIT(&v_empty[vs], ((vc / NV) & 1) ^ 1);
                     if (leader) {
                         mbar_arrive_expect_tx(&v_full[vs], KV_BYTES);
                         tma_load_4d(smem + OFF_V + vs * KV_BYTES, &tma_v, &v_full[vs], tok_base + (jj - 2) * KT, 0, h, b);
@@ -570,7 +617,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             pos += n;
             ++seg;
         }
-    } else if (warp >= W_MMA) {
+    } else if (warp >= W_MMA && warp < W_MMA + NISS) {
         // ------------- MMA issuers: warp W_MMA + ii serves the warpgroups i with i % NISS == ii -------------
         const int ii = warp - W_MMA;
         const bool leader = elect_one();
@@ -616,14 +663,17 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 const bool has2 = (jj + 2 < n);
                 const uint32_t vs = vc % NV;
                 const uint32_t ks = kc % NK;
-                mbar_wait_sleep(&v_full[vs], (vc / NV) & 1);
-                if (has2) mbar_wait_sleep(&k_full[ks], (kc / NK) & 1);
+                if (leader) CMT_TRACE(ii, g[ii], 6);
+                CMT_KV_WAIT(&v_full[vs], (vc / NV) & 1);
+                if (has2) CMT_KV_WAIT(&k_full[ks], (kc / NK) & 1);
+                if (leader) CMT_TRACE(ii, g[ii], 7);
                 const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * KV_BYTES), 128);
                 const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * KV_BYTES), 64);
 #pragma unroll
                 for (int i = 0; i < NWG; ++i) {
                     if ((i % NISS) == ii && i < nact) {
                         const uint32_t bsel = g[i] & 1;
+                        if (leader) CMT_TRACE(i, g[i], 11);
                         CMT_ISSUER_WAIT(&p_full[2 * i + bsel], (g[i] >> 1) & 1);
                         tc_fence_after();
                         if (leader) {
@@ -671,6 +721,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         uint64_t* my_s_full = s_full + 2 * wg;
         uint64_t* my_p_full = p_full + 2 * wg;
         const bool tracer = (threadIdx.x & 127) == 0;
+        uint64_t* my_tok = tok + wg * 4 + (warp & 3);
+        uint64_t* next_tok = tok + ((wg + 1) % NWG) * 4 + (warp & 3);
+        uint32_t turn = 0;                      // steps seen by this warp == token phases consumed
         uint32_t g = 0, seg = 0, pv_base = 0;   // pv_base: pv_done phases of the earlier segments (n - 1 each)
         for (long long pos = pos_begin; pos < pos_end;) {
             const int item = static_cast<int>(pos / p.T);
@@ -678,12 +731,37 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
             const int qb = item % p.qblocks;
             pos += n;
-            if (qb * QBLK + wg * 128 >= p.Nq) continue;     // this warpgroup's tile is past the last query
+            if (qb * QBLK + wg * 128 >= p.Nq) {             // this warpgroup's tile is past the last query
+                if (RING) {
+                    for (int jj = 0; jj < n; ++jj, ++turn) {
+                        CMT_TOK_WAIT(my_tok, turn & 1);
+                        if (lane == 0) mbar_arrive(next_tok);
+                    }
+                }
+                continue;
+            }
+            if (qb * QBLK + wg * 128 + (warp & 3) * 32 >= p.Nq) {
+                // all 32 rows of this warp are past the last query (900 queries: three warps of the eighth tile):
+                // keep the barrier protocol in step, skip the exponentials -- the MUFU pipe is the bound
+                for (int jj = 0; jj < n; ++jj, ++g) {
+                    if (RING) {
+                        CMT_TOK_WAIT(my_tok, turn & 1);
+                        if (lane == 0) mbar_arrive(next_tok);
+                        ++turn;
+                    }
+                    mbar_wait(&my_s_full[g & 1], (g >> 1) & 1);
+                    mbar_arrive(&my_p_full[g & 1]);
+                }
+                mbar_wait(&o_full[wg], seg & 1);
+                ++seg;
+                pv_base += n - 1;
+                continue;
+            }
             float m = -INFINITY, l = 0.0f;
             for (int jj = 0; jj < n; ++jj, ++g) {
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
-                mbar_wait(&my_s_full[bsel], (g >> 1) & 1);
+                CMT_S_WAIT(&my_s_full[bsel], (g >> 1) & 1);
                 if (tracer) CMT_TRACE(wg, g, 0);
                 tc_fence_after();
                 uint32_t s[2][32];
@@ -729,6 +807,11 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     }
                 }
                 if (tracer) CMT_TRACE(wg, g, 2);
+                if (RING) {
+                    CMT_TOK_WAIT(my_tok, turn & 1);
+                    ++turn;
+                }
+                if (tracer) CMT_TRACE(wg, g, 12);
                 // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs
                 const uint64_t neg_m2 = pack_f32x2(-m, -m);
                 uint64_t l2 = pack_f32x2(0.f, 0.f);
@@ -737,6 +820,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
+                        if (RING && c * 16 + i == RING_REL && lane == 0) mbar_arrive(next_tok);
                         const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
                         float e0, e1;
                         // one PAIR of exponentials in DB_POLY runs on the FMA pipes (packed cubic) instead of the MUFU
@@ -759,7 +843,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     l += l0 + l1;
                 }
                 tc_wait_st();
-                if (tracer) CMT_TRACE(wg, g, 3);
+                if (lane == 0) CMT_TRACE(wg, g, (warp & 3) == 0 ? 3 : 7 + (warp & 3));
                 tc_fence_before();
                 mbar_arrive(&my_p_full[bsel]);
             }
@@ -786,12 +870,13 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[3 * TRACE_STEPS * 8 + blockIdx.x] = clock64() - t_start;
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[3 * TRACE_STEPS * 16 + blockIdx.x] = clock64() - t_start;
     if (warp == W_TMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
 }
+
 
 // Merge the per-CTA segments of each item.  One thread = (item row, 4 output dims).
 template <bool kBf16>
@@ -859,7 +944,7 @@ static AttnVariant attn_variant() {
 static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid) {
     const AttnVariant var = attn_variant();
     p->qblk = var == kAttnWg2 ? attn::QBLK : attndb::QBLK;
-    p->kt = var == kAttnDb ? attndb::KT : attn::KT;
+    p->kt = var == kAttnWg2 ? attn::KT : attndb::KT;
     p->qblocks = (Nq + p->qblk - 1) / p->qblk;
     p->T = (n_tok + p->kt - 1) / p->kt;
     const long long items = static_cast<long long>(B) * H * p->qblocks;
@@ -868,7 +953,7 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p,
     // idle warpgroup it is bound by one warpgroup's own chain, ~3/4 of that
     p->w_full = 4;
     p->w_last = 4;
-    if (var == kAttnDb) {
+    if (var != kAttnWg2) {
         const int nact_last = (Nq - (p->qblocks - 1) * p->qblk + 127) / 128;
         if (nact_last < attndb::NWG) p->w_last = 3;
     }
@@ -883,8 +968,10 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p,
     *grid = static_cast<int>(G);
 }
 
-// Debug hook: device buffer of 3 * TRACE_STEPS * 8 int64 that CTA 0 of the three-warpgroup kernel fills with
-// clock64 stamps (tools/attn_trace.py).  nullptr switches the trace off.
+// Debug hook: device buffer of 3 * TRACE_STEPS * 16 + 148 int64.  Every CTA of tc_attn_db_kernel writes its total
+// cycle count into the last 148 entries (gives the SM clock under load); with -DCMT_ATTN_TRACE
+// (`make EXTRA=-DCMT_ATTN_TRACE`) CTA 0 also fills the per-step clock64 stamps (tools/attn_trace.py).
+// nullptr switches it off.
 static long long* g_trace_buf = nullptr;
 int tc_attn_set_timing_buffer(long long* dev_buf) { g_trace_buf = dev_buf; return CMT_OK; }
 
@@ -932,6 +1019,7 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn)");
         e = cudaFuncSetAttribute(tc_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
+
         attr_done = true;
     }
     CUtensorMap tq, tk, tv;

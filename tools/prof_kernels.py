@@ -1,5 +1,5 @@
 """Launch each hot kernel a few times at the nuScenes-multimodal shape (B=8) for an ncu capture.
-usage: python tools/prof_kernels.py [kproj|vproj|mlp1|mlp2|attn|gather|raype|all]"""
+usage: python tools/prof_kernels.py [kproj|vproj|mlp1|mlp2|attn|attnonly|gather|raype|all]"""
 import os
 import sys
 
@@ -40,6 +40,25 @@ if which in ("kproj", "vproj", "attn", "all"):
     if which in ("attn", "all"):
         q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
         timed("attn", lambda: ops.cross_attn(q, k, vt, 2))
+if which == "attnonly":   # attention alone on random K / V^T (A/B runs of kernel variants)
+    k = torch.randn(B, 1, H, N_kv, 32, device=dev).bfloat16()
+    vt = torch.randn(B, 1, H, 32, N_kv, device=dev).bfloat16()
+    q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
+    timed("attn", lambda: ops.cross_attn(q, k, vt, 0))
+    timed("attn", lambda: ops.cross_attn(q, k, vt, 0))
+    # per-CTA cycle counts of one launch -> SM clock under this kernel (power-limited, well below the 1965 MHz maximum)
+    import ctypes
+    from cmtcoop_b200 import _lib
+    lib = _lib.load()
+    lib.cmt_debug_attn_timing.argtypes = [ctypes.c_void_p]
+    buf = torch.zeros(3 * 96 * 16 + 148, dtype=torch.int64, device=dev)
+    lib.cmt_debug_attn_timing(ctypes.c_void_p(buf.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.cross_attn(q, k, vt, 0); e1.record(); torch.cuda.synchronize()
+    lib.cmt_debug_attn_timing(ctypes.c_void_p(0))
+    cyc = buf[3 * 96 * 16:].cpu().tolist()
+    us = e0.elapsed_time(e1) * 1e3
+    print(f"cycles/CTA median {sorted(cyc)[74]} max {max(cyc)}; {us:.0f} us -> SM clock >= {max(cyc) / us / 1e3:.3f} GHz", flush=True)
 if which in ("mlp1", "mlp2", "all"):
     M = 8 * 6 * 4000
     a = torch.randn(M, 192, device=dev).bfloat16()
