@@ -4,22 +4,12 @@
 // Replaces flash_attn_unpadded_kvpacked_func as called from
 // projects/mmdet3d_plugin/models/utils/attention.py:46-92 (softmax(QK^T/sqrt(d))V, non-causal).
 //
-// Work decomposition.  An "item" is (frame b, head h, block of 256 queries); it needs
-// T = ceil(n_tokens/128) KV tile-steps.  The flat space items x T is cut into gridDim.x equal
-// contiguous ranges (stream-K), one persistent CTA per SM, so that any batch size fills all 148
-// SMs; every (item, CTA) overlap ("segment") writes a normalised fp32 partial + log2-sum-exp into
-// the workspace and a second kernel merges the segments of each item.  The same partial/LSE
-// algebra serves the multi-GPU KV-token split (cmt_lse_merge).
-//
-// CTA layout (384 threads):
-//   warps 0-3   softmax warpgroup 0 : owns query rows   0..127 of the block (TMEM lanes = rows)
-//   warps 4-7   softmax warpgroup 1 : owns query rows 128..255
-//   warp  8     TMA producer        : Q (64B swizzle), K tiles [128 tok x 32] (64B swizzle),
-//                                     V^T tiles [32 x 128 tok] (two 128B-swizzle boxes), 4-stage rings
-//   warp  9     MMA issuer          : S_i = Q_i K^T  (tcgen05.mma SS, M128 N128 K16 x2)
-//                                     O_i += P_i V   (tcgen05.mma TS, A = P in TMEM, M128 N32 K16 x8)
-//   warp 10     TMEM allocator
-// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,416) O1 [416,448).
+// Work decomposition.  An "item" is (frame b, head h, block of queries: 128 for the default "iw" kernel); it
+// needs T = ceil(n_tokens/64) KV tile-steps.  The flat space items x T is cut into equal WEIGHTED contiguous
+// ranges (stream-K), three per persistent CTA (one per warpgroup), so that any batch size fills all 148 SMs;
+// every (item, range) overlap ("segment") writes a normalised fp32 partial + log2-sum-exp into the workspace and
+// a second kernel merges the segments of each item.  The same partial/LSE algebra serves the multi-GPU KV-token
+// split (cmt_lse_merge).  Kernel layouts are described at tc_attn_iw_kernel / tc_attn_db_kernel below.
 //
 // Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
 // rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
@@ -31,33 +21,6 @@
 
 namespace cmt {
 
-namespace attn {
-constexpr int QBLK = 256;
-constexpr int KT = 128;
-constexpr int NK = 4, NV = 4;
-constexpr int TILE_BYTES = 128 * 32 * 2;  // 8 KB: one Q tile, one K tile, one V^T tile
-constexpr int THREADS = 384;
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
-constexpr int OFF_V = OFF_K + NK * TILE_BYTES;
-constexpr int OFF_BAR = OFF_V + NV * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;
-constexpr float RESCALE_THRESHOLD = 8.0f;
-// The MUFU pipe (16 ex2 / clk / SM, measured: tools/microbench/exp_throughput.cu) is the bound of this kernel
-// at d_head = 32.  One in (2 * POLY_EVERY) exponentials is evaluated with a degree-3 polynomial on the
-// FMA/ALU pipes instead (12.7 / clk / SM measured), which are otherwise ~20 % busy.  0 disables.
-// Measured r1 (B=8, 56 400 tokens): POLY_EVERY=2 -> 1.36 ms per launch vs 1.26 ms without: the softmax warps
-// are issue/latency bound before they are MUFU bound, so the extra ~7 instructions per offloaded element
-// cost more than the MUFU slot they free.  Kept as a switch for the next round's restructured softmax.
-#ifndef CMT_ATTN_POLY_EVERY
-#define CMT_ATTN_POLY_EVERY 0
-#endif
-constexpr int POLY_EVERY = CMT_ATTN_POLY_EVERY;
-#ifndef CMT_ATTN_ALU_PACK
-#define CMT_ATTN_ALU_PACK 0
-#endif
-}  // namespace attn
 
 // 2^x for x <= ~8 on the FMA/ALU pipes: split x = n + f, f in [-0.5, 0.5] with the 1.5*2^23 rounding trick,
 // 2^f by the minimax cubic (relative error 7.5e-5, far below the 2^-9 rounding P gets anyway), 2^n by adding n to the
@@ -152,282 +115,6 @@ __device__ __forceinline__ long long range_start(const TcAttnParams& p, long lon
 __device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long long G) {
     const long long w = wpos_of(p, x);
     return static_cast<int>(((w + 1) * G + p.Wtot - 1) / p.Wtot - 1);
-}
-
-__global__ void __launch_bounds__(attn::THREADS, 1)
-tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-               const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
-    using namespace attn;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* q_full = bars + 0;
-    uint64_t* q_empty = bars + 1;
-    uint64_t* k_full = bars + 2;             // [NK]
-    uint64_t* k_empty = bars + 2 + NK;       // [NK]
-    uint64_t* v_full = bars + 2 + 2 * NK;    // [NV]
-    uint64_t* v_empty = v_full + NV;         // [NV]
-    uint64_t* s_full = v_empty + NV;         // [2]
-    uint64_t* p_full = s_full + 2;           // [2]
-    uint64_t* o_full = p_full + 2;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see tc_attn_db_kernel)
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 8 && lane == 0) {
-        tma_prefetch_desc(&tma_q);
-        tma_prefetch_desc(&tma_k);
-        tma_prefetch_desc(&tma_v);
-    }
-    if (warp == 9 && lane == 0) {
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
-        for (int s = 0; s < NK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-        for (int s = 0; s < NV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
-            mbar_init(&o_full[i], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 10) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-    const long long G = gridDim.x;
-    const long long pos_begin = range_start(p, blockIdx.x, G);
-    const long long pos_end = range_start(p, blockIdx.x + 1, G);
-
-    if (warp >= 8) {
-        setmaxnreg_dec<80>();
-        if (warp == 8) {
-            // ----------------------------- TMA producer -----------------------------
-            const bool leader = elect_one();
-            uint32_t kc = 0, vc = 0, seg = 0;
-            for (long long pos = pos_begin; pos < pos_end;) {
-                const int item = static_cast<int>(pos / p.T);
-                const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
-                const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-                const int qb = item % p.qblocks;
-                const int h = (item / p.qblocks) % p.H;
-                const int b = item / (p.qblocks * p.H);
-                mbar_wait(q_empty, (seg & 1) ^ 1);
-                if (leader) {
-                    mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-                    tma_load_4d(smem + OFF_Q, &tma_q, q_full, 0, qb * QBLK, h, b);
-                    tma_load_4d(smem + OFF_Q + TILE_BYTES, &tma_q, q_full, 0, qb * QBLK + 128, h, b);
-                }
-                for (int jj = 0; jj < n; ++jj) {
-                    const int tok0 = p.kv_begin + (j0 + jj) * KT;
-                    const uint32_t ks = kc % NK, vs = vc % NV;
-                    mbar_wait(&k_empty[ks], ((kc / NK) & 1) ^ 1);
-                    if (leader) {
-                        mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-                        tma_load_4d(smem + OFF_K + ks * TILE_BYTES, &tma_k, &k_full[ks], 0, tok0, h, b);
-                    }
-                    ++kc;
-                    mbar_wait(&v_empty[vs], ((vc / NV) & 1) ^ 1);
-                    if (leader) {
-                        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-                        uint8_t* sv = smem + OFF_V + vs * TILE_BYTES;
-                        tma_load_4d(sv, &tma_v, &v_full[vs], tok0, 0, h, b);
-                        tma_load_4d(sv + TILE_BYTES / 2, &tma_v, &v_full[vs], tok0 + 64, 0, h, b);
-                    }
-                    ++vc;
-                }
-                pos += n;
-                ++seg;
-            }
-        } else if (warp == 9) {
-            // ------------------------------ MMA issuer ------------------------------
-            const bool leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
-            const uint32_t sq = smem_u32(smem + OFF_Q);
-            uint32_t kc = 0, vc = 0, seg = 0;
-            uint32_t p_cnt[2] = {0, 0};
-            for (long long pos = pos_begin; pos < pos_end;) {
-                const int item = static_cast<int>(pos / p.T);
-                const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
-                const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-                mbar_wait(q_full, seg & 1);
-                {
-                    const uint32_t ks = kc % NK;
-                    mbar_wait(&k_full[ks], (kc / NK) & 1);
-                    tc_fence_after();
-                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
-                    if (leader) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
-                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
-                            tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
-                            tc_commit(&s_full[i]);
-                        }
-                        tc_commit(&k_empty[ks]);
-                        if (n == 1) tc_commit(q_empty);
-                    }
-                    __syncwarp();
-                    ++kc;
-                }
-                for (int jj = 0; jj < n; ++jj) {
-                    const bool has_next = (jj + 1 < n);
-                    const uint32_t vs = vc % NV;
-                    mbar_wait(&v_full[vs], (vc / NV) & 1);
-                    const uint32_t ks = kc % NK;
-                    if (has_next) mbar_wait(&k_full[ks], (kc / NK) & 1);
-                    tc_fence_after();
-                    const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + OFF_V + vs * TILE_BYTES), 128);
-                    const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + OFF_K + ks * TILE_BYTES), 64);
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        mbar_wait(&p_full[i], p_cnt[i] & 1);
-                        ++p_cnt[i];
-                        tc_fence_after();
-                        if (leader) {
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk) {
-                                const uint64_t vd = vdesc + (((kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32) >> 4);
-                                tc_mma_ts(tmem_base + COL_O + i * 32, tmem_base + COL_P + i * 64 + kk * 8, vd,
-                                          idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
-                            }
-                            if (has_next) {
-                                const uint64_t qdesc = make_kmajor_desc(sq + i * TILE_BYTES, 64);
-                                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc, kdesc, idesc_s, 0);
-                                tc_mma_ss(tmem_base + COL_S + i * 128, qdesc + 2, kdesc + 2, idesc_s, 1);
-                                tc_commit(&s_full[i]);
-                            } else {
-                                tc_commit(&o_full[i]);
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    if (leader) {
-                        tc_commit(&v_empty[vs]);
-                        if (has_next) {
-                            tc_commit(&k_empty[ks]);
-                            if (jj + 2 == n) tc_commit(q_empty);
-                        }
-                    }
-                    __syncwarp();
-                    ++vc;
-                    if (has_next) ++kc;
-                }
-                pos += n;
-                ++seg;
-            }
-        }
-    } else {
-        // --------------------------- softmax warpgroups ---------------------------
-        setmaxnreg_inc<200>();
-        const int wg = warp >> 2;                       // 0 or 1 -> Q tile
-        const int r = (warp & 3) * 32 + lane;           // row inside the 128-row tile == TMEM lane
-        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_base + COL_S + wg * 128;
-        const uint32_t t_p = tmem_base + lane_base + COL_P + wg * 64;
-        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
-        uint32_t tile_cnt = 0, seg = 0;
-        for (long long pos = pos_begin; pos < pos_end;) {
-            const int item = static_cast<int>(pos / p.T);
-            const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
-            const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-            float m = -INFINITY, l = 0.0f;
-            for (int jj = 0; jj < n; ++jj) {
-                mbar_wait(&s_full[wg], tile_cnt & 1);
-                ++tile_cnt;
-                tc_fence_after();
-                uint32_t s[4][32];
-                tmem_ld32(t_s + 0, s[0]);
-                tmem_ld32(t_s + 32, s[1]);
-                tmem_ld32(t_s + 64, s[2]);
-                tmem_ld32(t_s + 96, s[3]);
-                tc_wait_ld();
-                const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
-                if (valid < KT) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[2][i]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
-                }
-                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (jj == 0) {
-                    m = mx;  // O_i is overwritten by the first PV of the segment: nothing to rescale
-                } else {
-                    const bool need = (mx - m) > RESCALE_THRESHOLD;
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float m_new = need ? mx : m;
-                        const float alpha = ex2_approx(m - m_new);
-                        l *= alpha;
-                        uint32_t o[32];
-                        tmem_ld32(t_o, o);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(t_o, o);
-                        m = m_new;
-                    }
-                }
-                float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e0 = ex2_approx(__uint_as_float(s[c][2 * i]) - m);
-                        // every POLY_EVERY-th exponential runs on the FMA/ALU pipes instead of the MUFU
-                        const float x1 = __uint_as_float(s[c][2 * i + 1]) - m;
-                        const float e1 = (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x1) : ex2_approx(x1);
-                        l0 += e0;
-                        l1 += e1;
-                        pk[i] = pack_bf16x2(e0, e1);
-                    }
-                    tmem_st16(t_p + c * 16, pk);
-                }
-                l += l0 + l1;
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(&p_full[wg]);
-            }
-            // segment epilogue: normalised partial + log2-sum-exp into the workspace
-            mbar_wait(&o_full[wg], seg & 1);
-            tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(t_o, o);
-            tc_wait_ld();
-            const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(p, static_cast<long long>(item) * p.T, G));
-            const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
-            const float inv = 1.0f / l;
-            float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
-                                     __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
-            p.part_lse[prow] = m + log2f(l);
-            tc_fence_before();
-            pos += n;
-            ++seg;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 10) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -878,6 +565,381 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Independent-warpgroup variant ("iw", default).  In the db kernel the three warpgroups of a CTA share one
+// K/V stream, so they must work on the same (frame, head): with 900 = 7 * 128 + 4 queries the third query
+// block of every (frame, head) runs with one warpgroup idle and one almost idle, and that block still costs
+// ~3/4 of a full step (15 % of the kernel).  Here each warpgroup is a self-contained pipeline -- its own Q tile,
+// K/V stage ring, MMA issuer warp, score buffers and O accumulator -- and the unit of work is a 128-query tile:
+// the flat (tile, KV step) space is cut into 3 * gridDim.x weighted ranges, one per warpgroup "slot", so every
+// slot is busy with a full tile except while it holds one of the 4-query tail tiles (weight 3 of 5: the one
+// active warp is latency- rather than MUFU-bound).  K/V are read 3x more often from L2 (24 KB per CTA step),
+// but neighbouring slots walk neighbouring tiles of the same (frame, head) a few steps apart, so DRAM traffic
+// drops (one pass over K/V per (frame, head) instead of one per query block).
+//   smem per slot: Q 8 KB + 8 stages x (K 4 KB + V^T 4 KB); one full / one empty barrier per stage.
+//   512 threads: warps 0-11 softmax (slot = warp / 4), warp 12 TMA producer for the three streams (round-robin,
+//   non-blocking), warps 13-15 MMA issuers (one per slot, sleeping waits).
+//   TMEM as in the db kernel: S_i,b at [128 i + 64 b, +64), P over S, O_i at [384 + 32 i, +32).
+namespace attniw {
+using attndb::NWG;
+using attndb::KT;
+using attndb::Q_BYTES;
+using attndb::DB_POLY;
+using attndb::COL_O;
+using attndb::RESCALE_THRESHOLD;
+constexpr int QBLK = 128;                    // queries per item (one tile)
+constexpr int NST = 8;                       // K+V stages per slot
+constexpr int K_BYTES = 64 * 32 * 2;         // 4 KB K tile (64 tokens x 32 dims, 64B swizzle)
+constexpr int STAGE_BYTES = 2 * K_BYTES;     // + 4 KB V^T tile (32 dims x 64 tokens, 128B swizzle)
+constexpr int SLOT_BYTES = Q_BYTES + NST * STAGE_BYTES;
+constexpr int THREADS = NWG * 128 + 32 + NWG * 32;
+constexpr int OFF_BAR = NWG * SLOT_BYTES;
+constexpr int NBAR = 2 + 2 * NST + 6;        // per slot: q_full, q_empty, kv_full[], kv_empty[], s_full[2], p_full[2], pv_done, o_full
+constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
+static_assert(NWG * NBAR * 8 + 8 <= 1024, "barrier block");
+
+struct Seg {
+    int item, j0, n, qt, h, b;
+};
+__device__ __forceinline__ Seg decode_seg(const TcAttnParams& p, long long pos, long long pos_end) {
+    Seg s;
+    s.item = static_cast<int>(pos / p.T);
+    s.j0 = static_cast<int>(pos - static_cast<long long>(s.item) * p.T);
+    s.n = static_cast<int>(min(static_cast<long long>(p.T - s.j0), pos_end - pos));
+    s.qt = s.item % p.qblocks;
+    s.h = (s.item / p.qblocks) % p.H;
+    s.b = s.item / (p.qblocks * p.H);
+    return s;
+}
+}  // namespace attniw
+
+__global__ void __launch_bounds__(attniw::THREADS, 1)
+tc_attn_iw_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
+    using namespace attniw;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NWG * NBAR);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
+    constexpr int W_TMA = NWG * 4, W_MMA = NWG * 4 + 1;
+
+    if (warp == W_MMA && lane == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_v);
+        for (int i = 0; i < NWG; ++i) {
+            uint64_t* bw = bars + i * NBAR;
+            mbar_init(bw + 0, 1);   // q_full
+            mbar_init(bw + 1, 1);   // q_empty
+            for (int s = 0; s < 2 * NST; ++s) mbar_init(bw + 2 + s, 1);   // kv_full[], kv_empty[]
+            mbar_init(bw + 2 + 2 * NST + 0, 1);     // s_full[0]
+            mbar_init(bw + 2 + 2 * NST + 1, 1);     // s_full[1]
+            mbar_init(bw + 2 + 2 * NST + 2, 128);   // p_full[0]
+            mbar_init(bw + 2 + 2 * NST + 3, 128);   // p_full[1]
+            mbar_init(bw + 2 + 2 * NST + 4, 1);     // pv_done
+            mbar_init(bw + 2 + 2 * NST + 5, 1);     // o_full
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const long long t_start = p.trace != nullptr ? clock64() : 0;
+    const long long G = static_cast<long long>(gridDim.x) * NWG;   // slots
+
+    if (warp == W_TMA) {
+        // --------------- TMA producer: three independent streams, served round-robin by ONE thread ---------------
+        const bool leader = lane == 0;
+        long long pos[NWG], pend[NWG];
+        Seg sg[NWG];
+        int jj[NWG];
+        uint32_t kc[NWG], seg[NWG];
+        bool act[NWG], qdone[NWG];
+#pragma unroll
+        for (int w = 0; w < NWG; ++w) {
+            const long long sl = static_cast<long long>(blockIdx.x) * NWG + w;
+            pos[w] = range_start(p, sl, G);
+            pend[w] = range_start(p, sl + 1, G);
+            act[w] = pos[w] < pend[w];
+            if (act[w]) sg[w] = decode_seg(p, pos[w], pend[w]);
+            jj[w] = 0;
+            kc[w] = 0;
+            seg[w] = 0;
+            qdone[w] = false;
+        }
+        uint32_t idle_rounds = 0;
+        while (leader && (act[0] || act[1] || act[2])) {
+            bool progressed = false;
+#pragma unroll
+            for (int w = 0; w < NWG; ++w) {
+                if (!act[w]) continue;
+                uint64_t* bw = bars + w * NBAR;
+                uint8_t* sw = smem + w * SLOT_BYTES;
+                if (!qdone[w]) {
+                    if (!mbar_try_wait(bw + 1, (seg[w] & 1) ^ 1)) continue;   // q_empty
+                    if (leader) {
+                        mbar_arrive_expect_tx(bw + 0, Q_BYTES);
+                        tma_load_4d(sw, &tma_q, bw + 0, 0, sg[w].qt * QBLK, sg[w].h, sg[w].b);
+                    }
+                    qdone[w] = true;
+                    progressed = true;
+                }
+                const uint32_t st = kc[w] % NST;
+                if (!mbar_try_wait(bw + 2 + NST + st, ((kc[w] / NST) & 1) ^ 1)) continue;   // kv_empty[st]
+                if (leader) {
+                    uint8_t* dst = sw + Q_BYTES + st * STAGE_BYTES;
+                    const int tok = p.kv_begin + (sg[w].j0 + jj[w]) * KT;
+                    mbar_arrive_expect_tx(bw + 2 + st, STAGE_BYTES);
+                    tma_load_4d(dst, &tma_k, bw + 2 + st, 0, tok, sg[w].h, sg[w].b);
+                    tma_load_4d(dst + K_BYTES, &tma_v, bw + 2 + st, tok, 0, sg[w].h, sg[w].b);
+                }
+                progressed = true;
+                ++kc[w];
+                if (++jj[w] == sg[w].n) {
+                    pos[w] += sg[w].n;
+                    jj[w] = 0;
+                    ++seg[w];
+                    qdone[w] = false;
+                    act[w] = pos[w] < pend[w];
+                    if (act[w]) sg[w] = decode_seg(p, pos[w], pend[w]);
+                }
+            }
+            if (progressed) {
+                idle_rounds = 0;
+            } else {
+                __nanosleep(128);
+                if (++idle_rounds > CMT_SPIN_LIMIT) __trap();
+            }
+        }
+    } else if (warp >= W_MMA) {
+        // ------------------------- MMA issuer of slot i -------------------------
+        const int i = warp - W_MMA;
+        const bool leader = elect_one();
+        uint64_t* bw = bars + i * NBAR;
+        uint64_t* q_full = bw + 0;
+        uint64_t* q_empty = bw + 1;
+        uint64_t* kv_full = bw + 2;
+        uint64_t* kv_empty = bw + 2 + NST;
+        uint64_t* s_full = bw + 2 + 2 * NST;
+        uint64_t* p_full = s_full + 2;
+        uint64_t* pv_done = s_full + 4;
+        uint64_t* o_full = s_full + 5;
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
+        const uint32_t s_base = smem_u32(smem + i * SLOT_BYTES);
+        const uint64_t qdesc = make_kmajor_desc(s_base, 64);
+        const uint32_t t_s = tmem_base + i * 128;
+        const uint32_t t_o = tmem_base + COL_O + i * 32;
+        const long long sl = static_cast<long long>(blockIdx.x) * NWG + i;
+        const long long pos_end = range_start(p, sl + 1, G);
+        uint32_t kc = 0, seg = 0, g = 0;   // kc: stages consumed (S issue), g: steps retired (buffer = g & 1)
+        for (long long pos = range_start(p, sl, G); pos < pos_end;) {
+            const Seg sg = decode_seg(p, pos, pos_end);
+            const int n = sg.n;
+            mbar_wait_sleep(q_full, seg & 1);
+            // prologue: scores of steps 0 and 1 into the two buffers
+            for (int pre = 0; pre < 2 && pre < n; ++pre) {
+                const uint32_t ks = (kc + pre) % NST;
+                mbar_wait_sleep(&kv_full[ks], ((kc + pre) / NST) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t bsel = (g + pre) & 1;
+                    const uint64_t kdesc = make_kmajor_desc(s_base + Q_BYTES + ks * STAGE_BYTES, 64);
+                    tc_mma_ss(t_s + bsel * 64, qdesc, kdesc, idesc_s, 0);
+                    tc_mma_ss(t_s + bsel * 64, qdesc + 2, kdesc + 2, idesc_s, 1);
+                    tc_commit(&s_full[bsel]);
+                    if (pre + 1 == n) tc_commit(q_empty);
+                }
+                __syncwarp();
+            }
+            for (int jj = 0; jj < n; ++jj, ++g) {
+                const bool has2 = (jj + 2 < n);
+                const uint32_t vs = (kc + jj) % NST;          // stage of this step (V^T)
+                const uint32_t ks = (kc + jj + 2) % NST;      // stage of step jj + 2 (K)
+                if (has2) mbar_wait_sleep(&kv_full[ks], ((kc + jj + 2) / NST) & 1);
+                const uint32_t bsel = g & 1;
+                const uint64_t vdesc = make_kmajor_desc(s_base + Q_BYTES + vs * STAGE_BYTES + K_BYTES, 128);
+                const uint64_t kdesc = make_kmajor_desc(s_base + Q_BYTES + ks * STAGE_BYTES, 64);
+                if (leader) CMT_TRACE(i, g, 11);
+                mbar_wait_sleep(&p_full[bsel], (g >> 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    CMT_TRACE(i, g, 4);
+                    const uint32_t t_sp = t_s + bsel * 64;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_ts(t_o, t_sp + kk * 8, vdesc + kk * 2, idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
+                    if (jj + 1 == n) tc_commit(o_full);
+                    else tc_commit(pv_done);
+                    if (has2) {
+                        tc_mma_ss(t_sp, qdesc, kdesc, idesc_s, 0);
+                        tc_mma_ss(t_sp, qdesc + 2, kdesc + 2, idesc_s, 1);
+                        tc_commit(&s_full[bsel]);
+                        if (jj + 3 == n) tc_commit(q_empty);
+                    }
+                    tc_commit(&kv_empty[vs]);
+                    CMT_TRACE(i, g, 5);
+                }
+                __syncwarp();
+            }
+            kc += n;
+            pos += n;
+            ++seg;
+        }
+    } else {
+        // --------------------------- softmax warpgroup of slot wg ---------------------------
+        const int wg = warp >> 2;
+        const int r = (warp & 3) * 32 + lane;           // row inside the 128-row tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_base + wg * 128;   // + 64 * buffer
+        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
+        uint64_t* bw = bars + wg * NBAR;
+        uint64_t* s_full = bw + 2 + 2 * NST;
+        uint64_t* p_full = s_full + 2;
+        uint64_t* pv_done = s_full + 4;
+        uint64_t* o_full = s_full + 5;
+        const bool tracer = (threadIdx.x & 127) == 0;
+        (void)tracer;
+        const long long sl = static_cast<long long>(blockIdx.x) * NWG + wg;
+        const long long pos_end = range_start(p, sl + 1, G);
+        uint32_t g = 0, seg = 0, pv_base = 0;   // pv_base: pv_done phases of the earlier segments (n - 1 each)
+        for (long long pos = range_start(p, sl, G); pos < pos_end;) {
+            const Seg sg = decode_seg(p, pos, pos_end);
+            const int n = sg.n, j0 = sg.j0;
+            pos += n;
+            if (sg.qt * QBLK + (warp & 3) * 32 >= p.Nq) {
+                // all 32 rows of this warp are past the last query (the 4-query tail tile: three warps of four):
+                // keep the barrier protocol in step, skip the exponentials
+                for (int jj = 0; jj < n; ++jj, ++g) {
+                    mbar_wait_sleep(&s_full[g & 1], (g >> 1) & 1);
+                    mbar_arrive(&p_full[g & 1]);
+                }
+                mbar_wait_sleep(o_full, seg & 1);
+                ++seg;
+                pv_base += n - 1;
+                continue;
+            }
+            float m = -INFINITY, l = 0.0f;
+            for (int jj = 0; jj < n; ++jj, ++g) {
+                const uint32_t bsel = g & 1;
+                const uint32_t t_sb = t_s + bsel * 64;
+                CMT_S_WAIT(&s_full[bsel], (g >> 1) & 1);
+                if (tracer) CMT_TRACE(wg, g, 0);
+                tc_fence_after();
+                uint32_t s[2][32];
+                tmem_ld32(t_sb + 0, s[0]);
+                tmem_ld32(t_sb + 32, s[1]);
+                tc_wait_ld();
+                if (tracer) CMT_TRACE(wg, g, 1);
+                const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
+                if (valid < KT) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[0][16 + i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[1][i]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[1][16 + i]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (jj == 0) {
+                    m = mx;  // O is overwritten by the first PV of the segment: nothing to rescale
+                } else {
+                    const bool need = (mx - m) > RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // PV(step - 1) may still be accumulating into O: wait for it before touching O
+                        mbar_wait(pv_done, (pv_base + jj - 1) & 1);
+                        tc_fence_after();
+                        const float m_new = need ? mx : m;
+                        const float alpha = ex2_approx(m - m_new);
+                        l *= alpha;
+                        uint32_t o[32];
+                        tmem_ld32(t_o, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(t_o, o);
+                        m = m_new;
+                    }
+                }
+                if (tracer) CMT_TRACE(wg, g, 2);
+                if (tracer) CMT_TRACE(wg, g, 12);
+                // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs
+                const uint64_t neg_m2 = pack_f32x2(-m, -m);
+                uint64_t l2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
+                        float e0, e1;
+                        // one PAIR of exponentials in DB_POLY runs on the FMA pipes (packed cubic) instead of the MUFU
+                        if (DB_POLY > 0 && (i % (DB_POLY > 0 ? DB_POLY : 1)) == DB_POLY - 1) {
+                            ex2_poly_pair(x2, e0, e1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                        pk[i] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st16(t_sb + c * 16, pk);
+                }
+                {
+                    float l0, l1;
+                    unpack_f32x2(l2, l0, l1);
+                    l += l0 + l1;
+                }
+                tc_wait_st();
+                if (lane == 0) CMT_TRACE(wg, g, (warp & 3) == 0 ? 3 : 7 + (warp & 3));
+                tc_fence_before();
+                mbar_arrive(&p_full[bsel]);
+            }
+            // segment epilogue: normalised partial + log2-sum-exp into the workspace
+            mbar_wait(o_full, seg & 1);
+            ++seg;
+            pv_base += n - 1;
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld32(t_o, o);
+            tc_wait_ld();
+            const int slot = sg.item * p.S_max + (static_cast<int>(sl) - cta_of(p, static_cast<long long>(sg.item) * p.T, G));
+            const long long prow = static_cast<long long>(slot) * QBLK + r;
+            const float inv = 1.0f / l;
+            float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
+                                     __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
+            p.part_lse[prow] = m + log2f(l);
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[3 * TRACE_STEPS * 16 + blockIdx.x] = clock64() - t_start;
+    if (warp == W_TMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Merge the per-CTA segments of each item.  One thread = (item row, 4 output dims).
 template <bool kBf16>
 __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long long G, void* o,
@@ -928,44 +990,61 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
     }
 }
 
-// Kernel variant, read once per process from CMT_ATTN_VARIANT: "db" (default: three warpgroups, double-buffered
-// scores, 64-token tiles) or "wg2" (the first schedule: two warpgroups, 128-token tiles, single score buffer).
-enum AttnVariant { kAttnDb = 0, kAttnWg2 = 2 };
+// Kernel variant, read once per process from CMT_ATTN_VARIANT: "iw" (default: three independent warpgroup
+// pipelines, items of 128 queries) or "db" (three warpgroups sharing one K/V stream, items of 384 queries).
+enum AttnVariant { kAttnDb = 0, kAttnIw = 1 };
 static AttnVariant attn_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("CMT_ATTN_VARIANT");
         v = kAttnDb;
-        if (e != nullptr && strcmp(e, "wg2") == 0) v = kAttnWg2;
+        if (e != nullptr && strcmp(e, "iw") == 0) v = kAttnIw;
     }
     return static_cast<AttnVariant>(v);
 }
 
-static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid) {
+#ifndef CMT_ATTN_IW_WFULL
+#define CMT_ATTN_IW_WFULL 5
+#endif
+#ifndef CMT_ATTN_IW_WTAIL
+#define CMT_ATTN_IW_WTAIL 3
+#endif
+
+// Work plan.  G = number of weighted ranges ("slots": CTAs for db, warpgroups for iw); *grid = CTAs.
+static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid, long long* slots_out) {
     const AttnVariant var = attn_variant();
-    p->qblk = var == kAttnWg2 ? attn::QBLK : attndb::QBLK;
-    p->kt = var == kAttnWg2 ? attn::KT : attndb::KT;
+    const int per_cta = var == kAttnIw ? attniw::NWG : 1;
+    p->qblk = var == kAttnIw ? attniw::QBLK : attndb::QBLK;
+    p->kt = attndb::KT;
     p->qblocks = (Nq + p->qblk - 1) / p->qblk;
     p->T = (n_tok + p->kt - 1) / p->kt;
     const long long items = static_cast<long long>(B) * H * p->qblocks;
     p->W = items * p->T;
-    // step weights (measured, tools/attn_trace.py): with every warpgroup active a step is MUFU-bound; with an
-    // idle warpgroup it is bound by one warpgroup's own chain, ~3/4 of that
-    p->w_full = 4;
-    p->w_last = 4;
-    if (var != kAttnWg2) {
-        const int nact_last = (Nq - (p->qblocks - 1) * p->qblk + 127) / 128;
-        if (nact_last < attndb::NWG) p->w_last = 3;
+    const int rows_last = Nq - (p->qblocks - 1) * p->qblk;
+    if (var == kAttnIw) {
+        // step weights (measured): a full tile is MUFU-bound together with its two neighbours; a tile with one or two
+        // active warps is bound by its own chain (TMEM load, max, exponentials, store, barrier round trip)
+        p->w_full = CMT_ATTN_IW_WFULL;
+        p->w_last = rows_last <= 32 ? CMT_ATTN_IW_WTAIL : (rows_last <= 64 ? CMT_ATTN_IW_WFULL - 1 : CMT_ATTN_IW_WFULL);
+    } else {
+        // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
+        // own chain, ~3/4 of that
+        p->w_full = 4;
+        p->w_last = (rows_last + 127) / 128 < attndb::NWG ? 3 : 4;
     }
     p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
     p->Wtot = static_cast<long long>(B) * H * p->Wg;
-    // every CTA must own at least one step: weighted ranges no shorter than the widest step
-    long long G = sms;
-    if (G > p->Wtot / p->w_full) G = p->Wtot / p->w_full;
-    if (G < 1) G = 1;
-    const long long chunk_min = p->Wtot / G;  // >= w_full
+    // no more slots than full-weight steps, so that a range is never shorter than the widest step
+    long long ctas = sms;
+    const long long max_ctas = p->Wtot / p->w_full / per_cta;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    const long long G = ctas * per_cta;
+    long long chunk_min = p->Wtot / G;
+    if (chunk_min < 1) chunk_min = 1;
     p->S_max = static_cast<int>((static_cast<long long>(p->T) * p->w_full - 1) / chunk_min + 2);
-    *grid = static_cast<int>(G);
+    *grid = static_cast<int>(ctas);
+    *slots_out = G;
 }
 
 // Debug hook: device buffer of 3 * TRACE_STEPS * 16 + 148 int64.  Every CTA of tc_attn_db_kernel writes its total
@@ -979,13 +1058,13 @@ size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
     TcAttnParams p{};
     int grid;
-    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid);
+    long long G;
+    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid, &G);
     const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
     return slots * p.qblk * 33 * sizeof(float) + 256;
 }
 
 int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    using namespace attn;
     const int n_tok = a.kv_end - a.kv_begin;
     CMT_CHECK_ARG(n_tok > 0, "cmt_cross_attn_fwd: empty token range");
     CMT_CHECK_ARG(a.q_ld % 8 == 0 && a.v_ld % 8 == 0 && a.k_bstride % 8 == 0 && a.k_hstride % 8 == 0 &&
@@ -996,7 +1075,8 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
                   "cmt_cross_attn_fwd(bf16): pointers must be 16-byte aligned");
     TcAttnParams p{};
     int grid;
-    attn_plan(a.B, a.H, a.Nq, n_tok, device_sm_count(), &p, &grid);
+    long long G;
+    attn_plan(a.B, a.H, a.Nq, n_tok, device_sm_count(), &p, &grid, &G);
     p.B = a.B;
     p.H = a.H;
     p.Nq = a.Nq;
@@ -1015,8 +1095,8 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn)");
+        cudaError_t e = cudaFuncSetAttribute(tc_attn_iw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attniw::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_iw)");
         e = cudaFuncSetAttribute(tc_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
 
@@ -1048,16 +1128,16 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     if (attn_variant() == kAttnDb)
         tc_attn_db_kernel<<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     else
-        tc_attn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        tc_attn_iw_kernel<<<grid, attniw::THREADS, attniw::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
     const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * p.qblk * 8;
     long long mblocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(device_sm_count()) * 8;
     if (mblocks > cap) mblocks = cap;
     if (a.o_bf16)
-        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
+        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, G, a.o, a.lse);
     else
-        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, grid, a.o, a.lse);
+        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, G, a.o, a.lse);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(merge)");
     return CMT_OK;
 }

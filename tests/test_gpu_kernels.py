@@ -183,6 +183,9 @@ ATTN_CASES = [
     (1, 900, 5000, 0, None),      # reference query count, 4 query blocks, many CTAs per item
     (3, 257, 2049, 0, None),      # three query tiles -> two blocks, ragged everything
     (2, 200, 4096, 1024, 3000),   # KV sub-range (multi-GPU token split)
+    (1, 4, 64, 0, None),          # one tail tile, one step: fewer steps than warpgroup slots
+    (1, 1, 130, 0, None),         # a single query
+    (2, 388, 1500, 0, None),      # three full tiles + a 4-query tail tile (the 900 = 7*128+4 pattern)
 ]
 
 
