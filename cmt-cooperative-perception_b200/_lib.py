@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcmtcoop_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cmtcoop_b200.h")
 
 CMT_F32, CMT_BF16, CMT_BF16_SIMT = 0, 1, 3
-GEMM_RELU, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT = 1, 2, 4
+GEMM_RELU, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_TRANSPOSE_OUT = 1, 2, 4, 8
 
 _c = ctypes
 _vp, _i, _i64, _f, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t

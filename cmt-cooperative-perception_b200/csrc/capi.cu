@@ -212,6 +212,9 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
     g.relu = (flags & CMT_GEMM_RELU) ? 1 : 0;
     g.bias_per_row = (flags & CMT_GEMM_BIAS_PER_ROW) ? 1 : 0;
     g.out_bf16 = out_dtype == CMT_BF16;
+    g.transpose_c = (flags & CMT_GEMM_TRANSPOSE_OUT) ? 1 : 0;
+    CMT_CHECK_ARG(!g.transpose_c || (in_dtype == CMT_BF16 && !(flags & CMT_GEMM_FORCE_SIMT)),
+                  "cmt_gemm_bias_act: CMT_GEMM_TRANSPOSE_OUT is a bf16 tensor-core path option");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (in_dtype == CMT_BF16 && !(flags & CMT_GEMM_FORCE_SIMT)) return launch_tc_gemm(g, batch, s);
     return launch_simt_gemm(g, batch, in_dtype, s);

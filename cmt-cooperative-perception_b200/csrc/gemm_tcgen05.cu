@@ -3,12 +3,16 @@
 //   C = act((A * B^T + bias) * alpha),  A:[M,K] bf16, B:[N,K] bf16 (both K-major), fp32 accumulate.
 //
 // Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0      TMA producer  : 3-D tensor maps (K, rows, batch), 128B swizzle, 4-stage smem ring
+//   warp 0      TMA producer  : 3-D tensor maps (K, rows, batch), 128B swizzle.  Streaming mode: 4-stage ring of
+//                               A+B k-blocks.  B-resident mode (K <= 256, B not batched): the CTA's n-tile of B is
+//                               loaded once, the ring carries A only (5 stages).
 //   warp 1      MMA issuer    : one elected thread, tcgen05.mma cta_group::1 kind::f16,
 //                               M=128 x N=256 x K=16 per instruction, accumulator in TMEM
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, ping-pong)
-//   warps 4..11 epilogue      : tcgen05.ld 32x32b -> bias / alpha / ReLU -> bf16|fp32 -> global,
-//                               overlapped with the next tile's main loop
+//   warps 4..11 epilogue      : tcgen05.ld 32x32b -> bias (cached in shared memory) / alpha / ReLU -> bf16|fp32 ->
+//                               256-bit global stores straight from registers (a thread owns 32 consecutive
+//                               columns of one row: 64 / 128 contiguous bytes), overlapped with the next tile's
+//                               main loop.  No shared-memory staging: the MMAs already read 96 of the 128 B/clk.
 //
 // Replaces F.linear in models/utils/attention.py:21-27,138 and the PE MLPs of
 // models/dense_heads/cmt_head.py:292-301 (reference runs them as fp32 cuBLAS SGEMMs).
@@ -19,13 +23,32 @@ namespace cmt {
 
 namespace gemm {
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STORE_STAGING = 8 * 4096;  // per epilogue warp: two 32x32 bf16 tiles or one 32x32 fp32 tile
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+// B-resident mode (K <= 256, B shared by the batch): a CTA keeps ONE n-tile of B (all of K) in shared memory for its
+// whole life and streams only A tiles through the ring.  A 128x256 tile with K = 256 otherwise pulls 192 KB through
+// the TMA for 16.8 MFLOP (87 flop/B); with B resident a tile loads 64 KB (262 flop/B) and the n-tiles of one
+// m-tile run on neighbouring CTAs at the same time, so A comes from DRAM once and from L2 the other n_tiles - 1 times.
+constexpr int RES_KB = 4;                       // K blocks the resident B can hold (K <= 256)
+constexpr int B_RES_BYTES = RES_KB * B_BYTES;   // 128 KB
+#ifndef CMT_GEMM_RES_STAGES
+#define CMT_GEMM_RES_STAGES 5
+#endif
+constexpr int STREAM_STAGES = 4;                    // streaming mode: 4 x (A 16 KB + B 32 KB)
+constexpr int RES_STAGES = CMT_GEMM_RES_STAGES;     // B-resident mode: A-only stages of 16 KB after the 128 KB of B
+constexpr int MAX_STAGES = STREAM_STAGES > RES_STAGES ? STREAM_STAGES : RES_STAGES;
+constexpr int RING_BYTES = (STREAM_STAGES * STAGE_BYTES > B_RES_BYTES + RES_STAGES * A_BYTES)
+                               ? STREAM_STAGES * STAGE_BYTES : B_RES_BYTES + RES_STAGES * A_BYTES;
+// column bias cached in shared memory (the K/V projections have N = 1536): the epilogue's bias fetch becomes a
+// broadcast LDS instead of a ~500-cycle global load sitting between the TMEM load and the stores of a round
+constexpr int BIAS_CAP = 2048;
+constexpr int SMEM_BYTES = RING_BYTES + BIAS_CAP * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int THREADS = 384;  // 4 control warps + 8 epilogue warps
+#ifndef CMT_GEMM_WAIT
+#define CMT_GEMM_WAIT mbar_wait_sleep   // producer / accumulator hand-over waits: sleep in hardware, leave the issue slots to the epilogue
+#endif
 }  // namespace gemm
 
 struct TcGemmParams {
@@ -36,24 +59,63 @@ struct TcGemmParams {
     float alpha;
     int relu, bias_per_row, out_bf16;
     int a_batched, b_batched;
-    int tma_store;  // epilogue through shared memory + TMA tensor store (full-sector, coalesced writes)
-    int cb32;       // column block size as int (for the store coordinates)
     int m_tiles, n_tiles, total_tiles, num_kb;
+    int direct;     // 1: lean epilogue, 256-bit stores straight from registers (alignment / bias conditions hold)
+    int transpose_c; // 1: element (m, n) of batch z is stored at z*strideC + (n / cb)*cb_stride + (n % cb)*ldc + m (bf16)
+    int b_resident; // 1: gridDim.x = Gm * n_tiles, CTA c owns n-tile c % n_tiles and the (batch, m-tile) pairs c / n_tiles + i * Gm
+};
+
+// The three roles walk the same tile sequence.
+struct TileWalk {
+    int cur, step, end, nt_fixed;
+    __device__ __forceinline__ TileWalk(const TcGemmParams& p) {
+        if (p.b_resident) {
+            step = gridDim.x / p.n_tiles;
+            cur = blockIdx.x / p.n_tiles;
+            nt_fixed = blockIdx.x - cur * p.n_tiles;
+            end = p.total_tiles / p.n_tiles;   // batch * m_tiles
+        } else {
+            step = gridDim.x;
+            cur = blockIdx.x;
+            nt_fixed = -1;
+            end = p.total_tiles;
+        }
+    }
+    __device__ __forceinline__ bool valid() const { return cur < end; }
+    __device__ __forceinline__ void next() { cur += step; }
+    __device__ __forceinline__ void decode(const TcGemmParams& p, int& z, int& mt, int& nt) const {
+        if (nt_fixed >= 0) {
+            z = cur / p.m_tiles;
+            mt = cur - z * p.m_tiles;
+            nt = nt_fixed;
+        } else {
+            const int tiles_per_batch = p.m_tiles * p.n_tiles;
+            z = cur / tiles_per_batch;
+            const int r = cur - z * tiles_per_batch;
+            mt = r / p.n_tiles;
+            nt = r - mt * p.n_tiles;
+        }
+    }
 };
 
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const TcGemmParams p) {
+               const TcGemmParams p) {
     using namespace gemm;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* staging = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STORE_STAGING);
-    uint64_t* full_bar = bars;                   // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* bias_s = reinterpret_cast<float*>(smem + RING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + BIAS_CAP * 4);
+    uint64_t* full_bar = bars;                   // [MAX_STAGES]
+    uint64_t* empty_bar = bars + MAX_STAGES;     // [MAX_STAGES]
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;     // [2]
+    uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;  // [2]
+    uint64_t* bres_full = bars + 2 * MAX_STAGES + 4;   // resident B landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+    const int n_stages = p.b_resident ? RES_STAGES : STREAM_STAGES;
+    // ring geometry: streaming = 4 x (A 16 KB + B 32 KB); B-resident = B (128 KB) then RES_STAGES x A 16 KB
+    uint8_t* ring = p.b_resident ? smem + B_RES_BYTES : smem;
+    const int ring_stride = p.b_resident ? A_BYTES : STAGE_BYTES;
 
     // warp index / TMEM base through shuffles: provably warp-uniform, so the producer and issuer warps keep
     // their descriptors in uniform registers and TMA / tcgen05.mma instructions issue back to back (a divergent
@@ -66,7 +128,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -74,15 +136,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 8);  // one arrival per epilogue warp
         }
+        mbar_init(bres_full, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
+    const bool bias_cached = p.bias != nullptr && !p.bias_per_row && p.N <= BIAS_CAP - 64;
+    if (bias_cached)
+        for (int i = threadIdx.x; i < BIAS_CAP; i += THREADS) bias_s[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-    const int tiles_per_batch = p.m_tiles * p.n_tiles;
 
     if (warp == 0) {
         // ----------------------------- TMA producer -----------------------------
@@ -90,21 +154,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const bool leader = elect_one();
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int z = tile / tiles_per_batch;
-                const int r = tile - z * tiles_per_batch;
-                const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+            TileWalk w(p);
+            if (p.b_resident && w.valid() && leader) {
+                mbar_arrive_expect_tx(bres_full, p.num_kb * B_BYTES);
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    tma_load_3d(smem + kb * B_BYTES, &tma_b, bres_full, kb * BK, w.nt_fixed * BN, 0);
+            }
+            for (; w.valid(); w.next()) {
+                int z, mt, nt;
+                w.decode(p, z, mt, nt);
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    CMT_GEMM_WAIT(&empty_bar[stage], phase ^ 1);
                     if (leader) {
-                        uint8_t* sa = smem + stage * STAGE_BYTES;
-                        uint8_t* sb = sa + A_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
-                        tma_load_3d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                        uint8_t* sa = ring + stage * ring_stride;
+                        if (p.b_resident) {
+                            mbar_arrive_expect_tx(&full_bar[stage], A_BYTES);
+                            tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
+                            tma_load_3d(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                        }
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -117,17 +190,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            if (p.b_resident) {
+                mbar_wait_sleep(bres_full, 0);
+                tc_fence_after();
+            }
+            for (TileWalk w(p); w.valid(); w.next()) {
+                CMT_GEMM_WAIT(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (leader) {
-                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t sa = smem_u32(ring + stage * ring_stride);
                         const uint64_t adesc = make_kmajor_desc(sa, 128);
-                        const uint64_t bdesc = make_kmajor_desc(sa + A_BYTES, 128);
+                        const uint64_t bdesc = make_kmajor_desc(p.b_resident ? smem_u32(smem + kb * B_BYTES) : sa + A_BYTES, 128);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // +32 bytes per K=16 step inside the 128B swizzle atom (>>4 -> +2)
@@ -136,12 +213,124 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
                 if (leader) tc_commit(&tmem_full[acc]);
                 __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+        }
+    } else if (warp >= 4 && p.direct) {
+        // ------------------- epilogue, lean path: registers -> 256-bit global stores -------------------
+        // ncu on the K projection: l1tex (shared-memory) throughput 78 %, tensor pipe 42 %.  With cta_group::1 the MMAs
+        // alone read 96 B/clk of operands out of the 128 B/clk shared memory (A 4 KB + B 8 KB per 128-cycle
+        // instruction), so an epilogue that stages the tile in shared memory for a TMA store (64 KB written +
+        // 64 KB read per tile) competes for the kernel's scarcest resource.  A thread owns one output row and 32
+        // consecutive columns of it, i.e. 64 contiguous bytes of bf16 (128 of fp32) in EVERY layout this kernel
+        // writes: two (four) st.global.v8.b32 per chunk are full-sector writes with no staging at all.
+        // Transposed output (V^T: element (m, n) at (n % cb) * ldc + m): a warp instruction writes the 32 rows of
+        // one column, 64 contiguous bytes.
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const bool scale = p.alpha != 1.0f;
+        const bool relu = p.relu != 0;
+        const int esz = p.out_bf16 ? 2 : 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (TileWalk w(p); w.valid(); w.next()) {
+            int z, mt, nt;
+            w.decode(p, z, mt, nt);
+            const int m = mt * BM + quad * 32 + lane;
+            const bool m_ok = m < p.M;
+            const float row_bias = (p.bias != nullptr && p.bias_per_row && m_ok) ? __ldg(p.bias + m) : 0.0f;
+            // column block of the warp's first chunk: one division per tile, then +32 columns per chunk
+            const int n_first = nt * BN + half * (BN / 2);
+            long long nb = n_first / p.cb;
+            long long rem = n_first - nb * p.cb;
+            const long long row_off = z * p.strideC + (p.transpose_c ? static_cast<long long>(m) : static_cast<long long>(m) * p.ldc);
+            CMT_GEMM_WAIT(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+            for (int rd = 0; rd < 2; ++rd) {
+                const int n0 = n_first + rd * 64;
+                if (n0 >= p.N) break;   // warp-uniform (N % 32 == 0 on this path)
+                const bool has_b = n0 + 32 < p.N;
+                uint32_t v[2][32];
+                tmem_ld32(t_row + rd * 64, v[0]);
+                if (has_b) tmem_ld32(t_row + rd * 64 + 32, v[1]);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 1 && !has_b) break;
+                    float f[32];
+                    if (bias_cached) {
+                        const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = b4[i];
+                            f[4 * i] = b.x + __uint_as_float(v[c][4 * i]);
+                            f[4 * i + 1] = b.y + __uint_as_float(v[c][4 * i + 1]);
+                            f[4 * i + 2] = b.z + __uint_as_float(v[c][4 * i + 2]);
+                            f[4 * i + 3] = b.w + __uint_as_float(v[c][4 * i + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = row_bias + __uint_as_float(v[c][i]);
+                    }
+                    if (scale) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] *= p.alpha;
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+                    }
+                    const long long blk_off = nb * p.cb_stride;
+                    if (p.transpose_c) {
+                        // element (m, n) -> blk_off + (n % cb) * ldc + m  (bf16 only)
+                        uint16_t* dst = reinterpret_cast<uint16_t*>(p.C) + row_off + blk_off + rem * p.ldc;
+                        if (m_ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const uint32_t w2 = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+                                dst[static_cast<long long>(2 * i) * p.ldc] = static_cast<uint16_t>(w2 & 0xffffu);
+                                dst[static_cast<long long>(2 * i + 1) * p.ldc] = static_cast<uint16_t>(w2 >> 16);
+                            }
+                        }
+                    } else if (p.out_bf16) {
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + (row_off + blk_off + rem) * esz;
+                        if (m_ok) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * i),
+                                             "r"(pack_bf16x2(f[16 * i + 0], f[16 * i + 1])), "r"(pack_bf16x2(f[16 * i + 2], f[16 * i + 3])),
+                                             "r"(pack_bf16x2(f[16 * i + 4], f[16 * i + 5])), "r"(pack_bf16x2(f[16 * i + 6], f[16 * i + 7])),
+                                             "r"(pack_bf16x2(f[16 * i + 8], f[16 * i + 9])), "r"(pack_bf16x2(f[16 * i + 10], f[16 * i + 11])),
+                                             "r"(pack_bf16x2(f[16 * i + 12], f[16 * i + 13])), "r"(pack_bf16x2(f[16 * i + 14], f[16 * i + 15]))
+                                             : "memory");
+                        }
+                    } else {
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(p.C) + (row_off + blk_off + rem) * esz;
+                        if (m_ok) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * i),
+                                             "r"(__float_as_uint(f[8 * i + 0])), "r"(__float_as_uint(f[8 * i + 1])),
+                                             "r"(__float_as_uint(f[8 * i + 2])), "r"(__float_as_uint(f[8 * i + 3])),
+                                             "r"(__float_as_uint(f[8 * i + 4])), "r"(__float_as_uint(f[8 * i + 5])),
+                                             "r"(__float_as_uint(f[8 * i + 6])), "r"(__float_as_uint(f[8 * i + 7]))
+                                             : "memory");
+                        }
+                    }
+                    rem += 32;
+                    if (rem >= p.cb) { rem -= p.cb; ++nb; }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ------------------------------- epilogue -------------------------------
@@ -153,17 +342,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool has_bias = p.bias != nullptr;
         const bool col_bias = has_bias && !p.bias_per_row;
         const bool scale = p.alpha != 1.0f;
-        uint32_t store_cnt = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int z = tile / tiles_per_batch;
-            const int r = tile - z * tiles_per_batch;
-            const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+        for (TileWalk w(p); w.valid(); w.next()) {
+            int z, mt, nt;
+            w.decode(p, z, mt, nt);
             const int m = mt * BM + quad * 32 + lane;
             const bool m_ok = m < p.M;
             const float row_bias = (has_bias && p.bias_per_row && m_ok) ? __ldg(p.bias + m) : 0.0f;
-            mbar_wait(&tmem_full[acc], acc_phase);
+            CMT_GEMM_WAIT(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
             // column-block addressing without a 64-bit division per chunk: one division per tile, then the
@@ -175,7 +362,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const long long row_off = z * p.strideC + static_cast<long long>(m) * p.ldc;
             // bias for one 32-column chunk (independent of the accumulator: issued before the TMEM wait)
             auto load_bias = [&](int n0, float (&f)[32]) {
-                if (col_bias) {
+                if (bias_cached) {
+                    // n0 + 32 may pass N in the last tile: the extra values only reach columns the store clips
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = (n0 + 4 * i + 4 <= BIAS_CAP) ? b4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[4 * i] = b.x; f[4 * i + 1] = b.y; f[4 * i + 2] = b.z; f[4 * i + 3] = b.w;
+                    }
+                } else if (col_bias) {
                     if (n0 + 32 <= p.N) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);  // n0 % 32 == 0
 #pragma unroll
@@ -203,41 +398,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (p.relu) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-                }
-                if (p.tma_store) {
-                    // registers -> this warp's staging tile [32 rows][32 cols] -> one TMA tensor store.
-                    // A thread's direct 16-byte stores land in 64-byte-strided rows: half-filled sectors and
-                    // 32 sectors per request; the TMA store writes whole lines and clips the M / N tails itself.
-                    uint8_t* tile = staging + (warp - 4) * 4096 + (p.out_bf16 ? (store_cnt & 1) * 2048 : 0);
-                    if (lane == 0) {
-                        if (p.out_bf16) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-                    }
-                    __syncwarp();
-                    if (p.out_bf16) {
-                        uint4* row = reinterpret_cast<uint4*>(tile + lane * 64);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 w;
-                            w.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-                            w.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-                            w.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-                            w.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-                            row[i] = w;
-                        }
-                    } else {
-                        float4* row = reinterpret_cast<float4*>(tile + lane * 128);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) row[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int nb = n0 / p.cb32;
-                        tma_store_4d(&tma_c, tile, n0 - nb * p.cb32, mt * BM + quad * 32, nb, z);
-                        tma_store_commit();
-                    }
-                    ++store_cnt;
-                    return;
                 }
                 if (!m_ok) return;
                 if (p.out_bf16) {
@@ -295,7 +455,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.tma_store && lane == 0) tma_store_wait_all<0>();  // all tensor stores of this warp have landed
     }
 
     tc_fence_before();
@@ -347,32 +506,23 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
         if (rc) return rc;
     }
 
-    // C tensor map in "column block" coordinates (n % cb, m, n / cb, batch); used when the layout is TMA-able
-    CUtensorMap tc;
     const int esz = g.out_bf16 ? 2 : 4;
     const bool plain = g.cb >= g.N;
-    bool tma_store = (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc * esz) % 16 == 0 &&
-                     (plain || ((g.cb_stride * esz) % 16 == 0 && g.cb % 32 == 0)) &&
-                     (batch == 1 || (g.strideC * esz) % 16 == 0) && g.cb < (1ll << 31);
-    if (getenv("CMT_GEMM_NO_TMA_STORE")) tma_store = false;
-    if (tma_store) {
-        const uint64_t d0 = plain ? static_cast<uint64_t>(g.N) : static_cast<uint64_t>(g.cb);
-        const uint64_t d2 = plain ? 1 : static_cast<uint64_t>((g.N + g.cb - 1) / g.cb);
-        uint64_t dims[4] = {d0, static_cast<uint64_t>(g.M), d2, static_cast<uint64_t>(batch)};
-        uint64_t strides[3] = {static_cast<uint64_t>(g.ldc) * esz,
-                               static_cast<uint64_t>(plain ? g.M * g.ldc : g.cb_stride) * esz,
-                               static_cast<uint64_t>(batch > 1 ? g.strideC : (plain ? g.M * g.ldc : g.cb_stride * d2)) * esz};
-        uint32_t box[4] = {32, 32, 1, 1};
-        if (d0 < 32) box[0] = static_cast<uint32_t>(d0);
-        int rc = encode_tma(&tc, g.C, g.out_bf16 ? CMT_BF16 : CMT_F32, 4, dims, strides, box, 0);
-        if (rc) tma_store = false;  // fall back to direct stores (e.g. stride not encodable)
-        if (d0 < 32) tma_store = false;
-    }
-    if (!tma_store) tc = ta;  // unused placeholder
 
     TcGemmParams p{};
-    p.tma_store = tma_store ? 1 : 0;
-    p.cb32 = static_cast<int>(plain ? (1ll << 30) : g.cb);
+    p.transpose_c = g.transpose_c;
+    static const bool no_direct = getenv("CMT_GEMM_NO_DIRECT") != nullptr;
+    const bool bias_ok = g.bias == nullptr || g.bias_per_row || g.N <= BIAS_CAP - 64;
+    if (g.transpose_c) {
+        CMT_CHECK_ARG(g.out_bf16 && g.cb % 32 == 0 && g.N % 32 == 0 && bias_ok && !plain,
+                      "cmt_gemm_bias_act(bf16): transposed output needs bf16, cb %% 32 == 0, N %% 32 == 0, N <= %d", BIAS_CAP - 64);
+        p.direct = 1;
+    } else {
+        const bool aligned = (reinterpret_cast<uintptr_t>(g.C) & 31) == 0 && (g.ldc * esz) % 32 == 0 &&
+                             (plain || ((g.cb_stride * esz) % 32 == 0 && g.cb % 32 == 0)) &&
+                             (batch == 1 || (g.strideC * esz) % 32 == 0);
+        p.direct = (aligned && g.N % 32 == 0 && bias_ok && !no_direct) ? 1 : 0;
+    }
     p.bias = g.bias;
     p.C = g.C;
     p.M = g.M;
@@ -396,7 +546,15 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     p.num_kb = (g.K + BK - 1) / BK;
     int grid = device_sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);
+    const long long mz = static_cast<long long>(p.m_tiles) * batch;
+    static const bool no_resident = getenv("CMT_GEMM_NO_B_RESIDENT") != nullptr;
+    if (p.num_kb <= RES_KB && !p.b_batched && p.n_tiles <= device_sm_count() && !no_resident) {
+        long long gm = device_sm_count() / p.n_tiles;
+        if (gm > mz) gm = mz;
+        p.b_resident = 1;
+        grid = static_cast<int>(gm) * p.n_tiles;
+    }
+    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
     CMT_LAUNCH_CHECK("cmt_gemm_bias_act(tcgen05)");
     return CMT_OK;
 }

@@ -14,6 +14,7 @@ struct GemmArgs {
     long long strideA, strideB, strideC;
     float alpha;
     int relu, bias_per_row, out_bf16;
+    int transpose_c;   // bf16 tensor-core path only: store C^T inside each column block (see cmt_gemm_bias_act)
 };
 
 struct AttnArgs {

@@ -11,7 +11,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import CMT_BF16, CMT_BF16_SIMT, CMT_F32, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_RELU
+from ._lib import (CMT_BF16, CMT_BF16_SIMT, CMT_F32, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_RELU,
+                   GEMM_TRANSPOSE_OUT)
 
 HEAD_DIM = 32
 LOG2E = 1.4426950408889634
@@ -169,14 +170,15 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16)
 
 
 def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=1, strideA=0, strideB=0,
-         strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False):
+         strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False, transpose_out=False):
     """Raw cmt_gemm_bias_act: C = act((A B^T + bias) * alpha) with column-block output addressing."""
     A = _cuda(A, "A")
     Bm = _cuda(Bm, "B", A.dtype)
     C = _cuda(C, "C")
     if bias is not None:
         bias = _cuda(bias, "bias", torch.float32)
-    flags = (GEMM_RELU if relu else 0) | (GEMM_BIAS_PER_ROW if bias_per_row else 0) | (GEMM_FORCE_SIMT if force_simt else 0)
+    flags = ((GEMM_RELU if relu else 0) | (GEMM_BIAS_PER_ROW if bias_per_row else 0) |
+             (GEMM_FORCE_SIMT if force_simt else 0) | (GEMM_TRANSPOSE_OUT if transpose_out else 0))
     lib = _lib.load()
     with torch.cuda.device(A.device):
         rc = lib.cmt_gemm_bias_act(_ptr(A), _ptr(Bm), _ptr(bias), _ptr(C), M, N, K, lda, ldb, ldc,
@@ -223,8 +225,14 @@ def project_values_t(xv, w, bias, n_layers, H, out=None):
     ld = (N_kv + 7) // 8 * 8
     if out is None:
         out = torch.empty((B, n_layers, H, HEAD_DIM, ld), dtype=xv.dtype, device=xv.device)
-    gemm(w, xv, bias, out, NO, N_kv, C, lda=C, ldb=C, ldc=ld, batch=B, strideA=0, strideB=N_kv * C,
-         strideC=NO * ld, bias_per_row=True)
+    if xv.dtype == torch.bfloat16:
+        # tokens on the M side like the K projection (the CTA keeps its slice of W_v resident in shared memory and
+        # streams token tiles), each [tokens, 32] head block stored transposed
+        gemm(xv, w, bias, out, N_kv, NO, C, lda=C, ldb=C, ldc=ld, cb=HEAD_DIM, cb_stride=HEAD_DIM * ld, batch=B,
+             strideA=N_kv * C, strideB=0, strideC=NO * ld, transpose_out=True)
+    else:
+        gemm(w, xv, bias, out, NO, N_kv, C, lda=C, ldb=C, ldc=ld, batch=B, strideA=0, strideB=N_kv * C,
+             strideC=NO * ld, bias_per_row=True)
     return out
 
 

@@ -36,6 +36,7 @@ extern "C" {
 #define CMT_GEMM_RELU 1          /* out = max(out, 0)                                  */
 #define CMT_GEMM_BIAS_PER_ROW 2  /* bias indexed by output row (default: by column)    */
 #define CMT_GEMM_FORCE_SIMT 4    /* fp32 CUDA-core kernel even for bf16 operands       */
+#define CMT_GEMM_TRANSPOSE_OUT 8 /* store C^T inside each column block (bf16 tensor-core path only) */
 
 int cmt_version(void);
 const char* cmt_last_error_string(void);
@@ -91,7 +92,11 @@ int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_p
  * Output addressing ("column blocks"): element (m,n) of batch z is stored at
  *     C + z*strideC + (n / cb)*cb_stride + m*ldc + (n % cb)
  * cb >= N gives a plain row-major matrix; cb = 32 with ldc = 32 gives the per-head
- * [.., H, tokens, 32] layout the attention kernel reads.
+ * [.., H, tokens, 32] layout the attention kernel reads.  With CMT_GEMM_TRANSPOSE_OUT the block is
+ * written transposed,
+ *     C + z*strideC + (n / cb)*cb_stride + (n % cb)*ldc + m
+ * which with cb = 32, ldc = ld gives the token-contiguous V^T layout [.., H, 32, ld] (bf16 operands and
+ * output, cb % 32 == 0, N % 32 == 0, N <= 1984).
  * in_dtype bf16 -> TMA + tcgen05 kernel (fp32 accumulate in TMEM); in_dtype fp32 -> fp32
  * CUDA-core kernel (verification mode).  Requirements for bf16: K % 8 == 0, lda/ldb % 8 == 0,
  * 16-byte aligned bases, and (cb >= N or cb % 32 == 0). */
