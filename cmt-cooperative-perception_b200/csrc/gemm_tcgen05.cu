@@ -235,6 +235,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool scale = p.alpha != 1.0f;
         const bool relu = p.relu != 0;
         const int esz = p.out_bf16 ? 2 : 4;
+        const uint32_t bias_addr = smem_u32(bias_s);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (TileWalk w(p); w.valid(); w.next()) {
@@ -251,32 +252,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             CMT_GEMM_WAIT(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-#pragma unroll 1
-            for (int rd = 0; rd < 2; ++rd) {
-                const int n0 = n_first + rd * 64;
-                if (n0 >= p.N) break;   // warp-uniform (N % 32 == 0 on this path)
-                const bool has_b = n0 + 32 < p.N;
-                uint32_t v[2][32];
-                tmem_ld32(t_row + rd * 64, v[0]);
-                if (has_b) tmem_ld32(t_row + rd * 64 + 32, v[1]);
+            // software pipeline over the warp's four 32-column chunks: the TMEM load of chunk c + 1 is in flight while
+            // chunk c is biased / packed / stored (tcgen05.wait::ld waits for every outstanding load, so the wait
+            // comes after the work on the current chunk)
+            const int n_chunks = min(4, (p.N - n_first + 31) >> 5);   // warp-uniform; <= 0: nothing to do
+            uint32_t v[2][32];
+            if (n_chunks > 0) {
+                tmem_ld32(t_row, v[0]);
                 tc_wait_ld();
+            }
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (c == 1 && !has_b) break;
+            for (int c = 0; c < 4; ++c) {
+                if (c >= n_chunks) break;
+                if (c + 1 < n_chunks) tmem_ld32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+                const int n0 = n_first + c * 32;
+                {
                     float f[32];
+                    const uint32_t (&vc)[32] = v[c & 1];
                     if (bias_cached) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c * 32);
+                        const uint32_t baddr = bias_addr + n0 * 4;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 b = b4[i];
-                            f[4 * i] = b.x + __uint_as_float(v[c][4 * i]);
-                            f[4 * i + 1] = b.y + __uint_as_float(v[c][4 * i + 1]);
-                            f[4 * i + 2] = b.z + __uint_as_float(v[c][4 * i + 2]);
-                            f[4 * i + 3] = b.w + __uint_as_float(v[c][4 * i + 3]);
+                            float4 b;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(baddr + i * 16));
+                            f[4 * i] = b.x + __uint_as_float(vc[4 * i]);
+                            f[4 * i + 1] = b.y + __uint_as_float(vc[4 * i + 1]);
+                            f[4 * i + 2] = b.z + __uint_as_float(vc[4 * i + 2]);
+                            f[4 * i + 3] = b.w + __uint_as_float(vc[4 * i + 3]);
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = row_bias + __uint_as_float(v[c][i]);
+                        for (int i = 0; i < 32; ++i) f[i] = row_bias + __uint_as_float(vc[i]);
                     }
                     if (scale) {
 #pragma unroll
@@ -326,6 +332,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     rem += 32;
                     if (rem >= p.cb) { rem -= p.cb; ++nb; }
                 }
+                if (c + 1 < n_chunks) tc_wait_ld();
             }
             tc_fence_before();
             __syncwarp();
