@@ -4,12 +4,12 @@
 // Replaces flash_attn_unpadded_kvpacked_func as called from
 // projects/mmdet3d_plugin/models/utils/attention.py:46-92 (softmax(QK^T/sqrt(d))V, non-causal).
 //
-// Work decomposition.  An "item" is (frame b, head h, block of queries: 128 for the default "iw" kernel); it
-// needs T = ceil(n_tokens/64) KV tile-steps.  The flat space items x T is cut into equal WEIGHTED contiguous
-// ranges (stream-K), three per persistent CTA (one per warpgroup), so that any batch size fills all 148 SMs;
+// Work decomposition.  An "item" is (frame b, head h, block of 384 queries = three 128-row tiles, one per softmax
+// warpgroup); it needs T = ceil(n_tokens/64) KV tile-steps.  The flat space items x T is cut into equal WEIGHTED
+// contiguous ranges (stream-K), one per persistent CTA, so that any batch size fills all 148 SMs;
 // every (item, range) overlap ("segment") writes a normalised fp32 partial + log2-sum-exp into the workspace and
 // a second kernel merges the segments of each item.  The same partial/LSE algebra serves the multi-GPU KV-token
-// split (cmt_lse_merge).  Kernel layouts are described at tc_attn_iw_kernel / tc_attn_db_kernel below.
+// split (cmt_lse_merge).  The kernel layout is described at tc_attn_db_kernel below.
 //
 // Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
 // rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
@@ -62,7 +62,7 @@ struct TcAttnParams {
     int B, H, Nq;
     int kv_begin, kv_end;
     int T;            // KV tile-steps per item
-    int qblk;         // queries per item: 256 (two softmax warpgroups) or 384 (three)
+    int qblk;         // queries per item: 384 (three softmax warpgroups)
     int kt;           // KV tokens per tile-step: 128, or 64 for the double-buffered kernel
     int qblocks;      // ceil(Nq / qblk)
     long long W;      // items * T
@@ -74,6 +74,9 @@ struct TcAttnParams {
     int S_max;        // partial slots per item
     float* part_o;    // [items*S_max][qblk][32]
     float* part_lse;  // [items*S_max][qblk]   (log2 domain)
+    // key padding mask (attention.py:76-90): bit i of mask_bits[b * T + j] = key kv_begin + 64 j + i of frame b is
+    // attended (and < kv_end); nullptr = no mask.  Packed from the byte mask by pack_key_mask_kernel.
+    const unsigned long long* mask_bits;
     long long* trace; // debug: clock64 event trace of CTA 0 (three-warpgroup kernel), nullptr = off
 };
 constexpr int TRACE_STEPS = 96;
@@ -130,6 +133,21 @@ __device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long l
 //   512 threads: warps 0-11 softmax (one query row per thread, 64 scores in registers), 12 TMA + TMEM
 //   allocation, 13-15 one MMA issuer per warpgroup.  No setmaxnreg: 128 registers per thread are enough
 //   for 64-column tiles.
+// One thread = one 64-key tile of one frame: byte mask -> bit mask, tail beyond kv_end cleared.
+__global__ void pack_key_mask_kernel(const unsigned char* keep, unsigned long long* bits, int B, int N_kv, int kv_begin,
+                                     int kv_end, int T) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(B) * T) return;
+    const int b = static_cast<int>(idx / T), j = static_cast<int>(idx - static_cast<long long>(b) * T);
+    const int t0 = kv_begin + j * 64;
+    unsigned long long m = 0;
+    for (int i = 0; i < 64; ++i) {
+        const int t = t0 + i;
+        if (t < kv_end && keep[static_cast<long long>(b) * N_kv + t] != 0) m |= 1ull << i;
+    }
+    bits[idx] = m;
+}
+
 namespace attndb {
 #ifndef CMT_ATTN_NWG
 #define CMT_ATTN_NWG 3
@@ -201,6 +219,9 @@ constexpr bool RING = CMT_ATTN_RING != 0;
 constexpr int RING_REL = CMT_ATTN_RING_REL;
 }  // namespace attndb
 
+// kMask: key padding mask variant (the unmasked instantiation carries none of its code: even an untaken mask
+// branch in the softmax loop cost 12 % on the 128-register budget).
+template <bool kMask>
 __global__ void __launch_bounds__(attndb::THREADS, 1)
 tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
@@ -445,6 +466,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 continue;
             }
             float m = -INFINITY, l = 0.0f;
+            const unsigned long long* mask_row = kMask ? p.mask_bits + static_cast<long long>(item / (p.qblocks * p.H)) * p.T : nullptr;
             for (int jj = 0; jj < n; ++jj, ++g) {
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
@@ -457,7 +479,16 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 tc_wait_ld();
                 if (tracer) CMT_TRACE(wg, g, 1);
                 const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
-                if (valid < KT) {
+                if (kMask) {
+                    // padded keys (and the tail past kv_end, folded into the bit mask) score -inf
+                    const unsigned long long mb = __ldg(mask_row + j0 + jj);
+                    const uint32_t mlo = static_cast<uint32_t>(mb), mhi = static_cast<uint32_t>(mb >> 32);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (!((mlo >> i) & 1u)) s[0][i] = 0xff800000u;
+                        if (!((mhi >> i) & 1u)) s[1][i] = 0xff800000u;
+                    }
+                } else if (valid < KT) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -474,7 +505,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 }
                 const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 if (jj == 0) {
-                    m = mx;  // O_i is overwritten by the first PV of the segment: nothing to rescale
+                    // O_i is overwritten by the first PV of the segment: nothing to rescale.  A first tile whose keys
+                    // are all padding has mx = -inf: keep m finite so that x - m stays -inf (weight 0), never NaN.
+                    m = kMask ? fmaxf(mx, -1e30f) : mx;
                 } else {
                     const bool need = (mx - m) > RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, need)) {
@@ -544,7 +577,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             tc_wait_ld();
             const int slot = item * p.S_max + (static_cast<int>(blockIdx.x) - cta_of(p, static_cast<long long>(item) * p.T, G));
             const long long prow = static_cast<long long>(slot) * QBLK + wg * 128 + r;
-            const float inv = 1.0f / l;
+            const float inv = l > 0.0f ? 1.0f / l : 0.0f;   // l == 0: every key of the segment was padding
             float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -564,381 +597,6 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// Independent-warpgroup variant ("iw", default).  In the db kernel the three warpgroups of a CTA share one
-// K/V stream, so they must work on the same (frame, head): with 900 = 7 * 128 + 4 queries the third query
-// block of every (frame, head) runs with one warpgroup idle and one almost idle, and that block still costs
-// ~3/4 of a full step (15 % of the kernel).  Here each warpgroup is a self-contained pipeline -- its own Q tile,
-// K/V stage ring, MMA issuer warp, score buffers and O accumulator -- and the unit of work is a 128-query tile:
-// the flat (tile, KV step) space is cut into 3 * gridDim.x weighted ranges, one per warpgroup "slot", so every
-// slot is busy with a full tile except while it holds one of the 4-query tail tiles (weight 3 of 5: the one
-// active warp is latency- rather than MUFU-bound).  K/V are read 3x more often from L2 (24 KB per CTA step),
-// but neighbouring slots walk neighbouring tiles of the same (frame, head) a few steps apart, so DRAM traffic
-// drops (one pass over K/V per (frame, head) instead of one per query block).
-//   smem per slot: Q 8 KB + 8 stages x (K 4 KB + V^T 4 KB); one full / one empty barrier per stage.
-//   512 threads: warps 0-11 softmax (slot = warp / 4), warp 12 TMA producer for the three streams (round-robin,
-//   non-blocking), warps 13-15 MMA issuers (one per slot, sleeping waits).
-//   TMEM as in the db kernel: S_i,b at [128 i + 64 b, +64), P over S, O_i at [384 + 32 i, +32).
-namespace attniw {
-using attndb::NWG;
-using attndb::KT;
-using attndb::Q_BYTES;
-using attndb::DB_POLY;
-using attndb::COL_O;
-using attndb::RESCALE_THRESHOLD;
-constexpr int QBLK = 128;                    // queries per item (one tile)
-constexpr int NST = 8;                       // K+V stages per slot
-constexpr int K_BYTES = 64 * 32 * 2;         // 4 KB K tile (64 tokens x 32 dims, 64B swizzle)
-constexpr int STAGE_BYTES = 2 * K_BYTES;     // + 4 KB V^T tile (32 dims x 64 tokens, 128B swizzle)
-constexpr int SLOT_BYTES = Q_BYTES + NST * STAGE_BYTES;
-constexpr int THREADS = NWG * 128 + 32 + NWG * 32;
-constexpr int OFF_BAR = NWG * SLOT_BYTES;
-constexpr int NBAR = 2 + 2 * NST + 6;        // per slot: q_full, q_empty, kv_full[], kv_empty[], s_full[2], p_full[2], pv_done, o_full
-constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
-static_assert(NWG * NBAR * 8 + 8 <= 1024, "barrier block");
-
-struct Seg {
-    int item, j0, n, qt, h, b;
-};
-__device__ __forceinline__ Seg decode_seg(const TcAttnParams& p, long long pos, long long pos_end) {
-    Seg s;
-    s.item = static_cast<int>(pos / p.T);
-    s.j0 = static_cast<int>(pos - static_cast<long long>(s.item) * p.T);
-    s.n = static_cast<int>(min(static_cast<long long>(p.T - s.j0), pos_end - pos));
-    s.qt = s.item % p.qblocks;
-    s.h = (s.item / p.qblocks) % p.H;
-    s.b = s.item / (p.qblocks * p.H);
-    return s;
-}
-}  // namespace attniw
-
-__global__ void __launch_bounds__(attniw::THREADS, 1)
-tc_attn_iw_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                  const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
-    using namespace attniw;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NWG * NBAR);
-
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-    const int lane = threadIdx.x & 31;
-    constexpr int W_TMA = NWG * 4, W_MMA = NWG * 4 + 1;
-
-    if (warp == W_MMA && lane == 0) {
-        tma_prefetch_desc(&tma_q);
-        tma_prefetch_desc(&tma_k);
-        tma_prefetch_desc(&tma_v);
-        for (int i = 0; i < NWG; ++i) {
-            uint64_t* bw = bars + i * NBAR;
-            mbar_init(bw + 0, 1);   // q_full
-            mbar_init(bw + 1, 1);   // q_empty
-            for (int s = 0; s < 2 * NST; ++s) mbar_init(bw + 2 + s, 1);   // kv_full[], kv_empty[]
-            mbar_init(bw + 2 + 2 * NST + 0, 1);     // s_full[0]
-            mbar_init(bw + 2 + 2 * NST + 1, 1);     // s_full[1]
-            mbar_init(bw + 2 + 2 * NST + 2, 128);   // p_full[0]
-            mbar_init(bw + 2 + 2 * NST + 3, 128);   // p_full[1]
-            mbar_init(bw + 2 + 2 * NST + 4, 1);     // pv_done
-            mbar_init(bw + 2 + 2 * NST + 5, 1);     // o_full
-        }
-        fence_barrier_init();
-    }
-    if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-    const long long t_start = p.trace != nullptr ? clock64() : 0;
-    const long long G = static_cast<long long>(gridDim.x) * NWG;   // slots
-
-    if (warp == W_TMA) {
-        // --------------- TMA producer: three independent streams, served round-robin by ONE thread ---------------
-        const bool leader = lane == 0;
-        long long pos[NWG], pend[NWG];
-        Seg sg[NWG];
-        int jj[NWG];
-        uint32_t kc[NWG], seg[NWG];
-        bool act[NWG], qdone[NWG];
-#pragma unroll
-        for (int w = 0; w < NWG; ++w) {
-            const long long sl = static_cast<long long>(blockIdx.x) * NWG + w;
-            pos[w] = range_start(p, sl, G);
-            pend[w] = range_start(p, sl + 1, G);
-            act[w] = pos[w] < pend[w];
-            if (act[w]) sg[w] = decode_seg(p, pos[w], pend[w]);
-            jj[w] = 0;
-            kc[w] = 0;
-            seg[w] = 0;
-            qdone[w] = false;
-        }
-        uint32_t idle_rounds = 0;
-        while (leader && (act[0] || act[1] || act[2])) {
-            bool progressed = false;
-#pragma unroll
-            for (int w = 0; w < NWG; ++w) {
-                if (!act[w]) continue;
-                uint64_t* bw = bars + w * NBAR;
-                uint8_t* sw = smem + w * SLOT_BYTES;
-                if (!qdone[w]) {
-                    if (!mbar_try_wait(bw + 1, (seg[w] & 1) ^ 1)) continue;   // q_empty
-                    if (leader) {
-                        mbar_arrive_expect_tx(bw + 0, Q_BYTES);
-                        tma_load_4d(sw, &tma_q, bw + 0, 0, sg[w].qt * QBLK, sg[w].h, sg[w].b);
-                    }
-                    qdone[w] = true;
-                    progressed = true;
-                }
-                const uint32_t st = kc[w] % NST;
-                if (!mbar_try_wait(bw + 2 + NST + st, ((kc[w] / NST) & 1) ^ 1)) continue;   // kv_empty[st]
-                if (leader) {
-                    uint8_t* dst = sw + Q_BYTES + st * STAGE_BYTES;
-                    const int tok = p.kv_begin + (sg[w].j0 + jj[w]) * KT;
-                    mbar_arrive_expect_tx(bw + 2 + st, STAGE_BYTES);
-                    tma_load_4d(dst, &tma_k, bw + 2 + st, 0, tok, sg[w].h, sg[w].b);
-                    tma_load_4d(dst + K_BYTES, &tma_v, bw + 2 + st, tok, 0, sg[w].h, sg[w].b);
-                }
-                progressed = true;
-                ++kc[w];
-                if (++jj[w] == sg[w].n) {
-                    pos[w] += sg[w].n;
-                    jj[w] = 0;
-                    ++seg[w];
-                    qdone[w] = false;
-                    act[w] = pos[w] < pend[w];
-                    if (act[w]) sg[w] = decode_seg(p, pos[w], pend[w]);
-                }
-            }
-            if (progressed) {
-                idle_rounds = 0;
-            } else {
-                __nanosleep(128);
-                if (++idle_rounds > CMT_SPIN_LIMIT) __trap();
-            }
-        }
-    } else if (warp >= W_MMA) {
-        // ------------------------- MMA issuer of slot i -------------------------
-        const int i = warp - W_MMA;
-        const bool leader = elect_one();
-        uint64_t* bw = bars + i * NBAR;
-        uint64_t* q_full = bw + 0;
-        uint64_t* q_empty = bw + 1;
-        uint64_t* kv_full = bw + 2;
-        uint64_t* kv_empty = bw + 2 + NST;
-        uint64_t* s_full = bw + 2 + 2 * NST;
-        uint64_t* p_full = s_full + 2;
-        uint64_t* pv_done = s_full + 4;
-        uint64_t* o_full = s_full + 5;
-        constexpr uint32_t idesc_s = make_idesc_bf16(128, KT);
-        constexpr uint32_t idesc_o = make_idesc_bf16(128, 32);
-        const uint32_t s_base = smem_u32(smem + i * SLOT_BYTES);
-        const uint64_t qdesc = make_kmajor_desc(s_base, 64);
-        const uint32_t t_s = tmem_base + i * 128;
-        const uint32_t t_o = tmem_base + COL_O + i * 32;
-        const long long sl = static_cast<long long>(blockIdx.x) * NWG + i;
-        const long long pos_end = range_start(p, sl + 1, G);
-        uint32_t kc = 0, seg = 0, g = 0;   // kc: stages consumed (S issue), g: steps retired (buffer = g & 1)
-        for (long long pos = range_start(p, sl, G); pos < pos_end;) {
-            const Seg sg = decode_seg(p, pos, pos_end);
-            const int n = sg.n;
-            mbar_wait_sleep(q_full, seg & 1);
-            // prologue: scores of steps 0 and 1 into the two buffers
-            for (int pre = 0; pre < 2 && pre < n; ++pre) {
-                const uint32_t ks = (kc + pre) % NST;
-                mbar_wait_sleep(&kv_full[ks], ((kc + pre) / NST) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t bsel = (g + pre) & 1;
-                    const uint64_t kdesc = make_kmajor_desc(s_base + Q_BYTES + ks * STAGE_BYTES, 64);
-                    tc_mma_ss(t_s + bsel * 64, qdesc, kdesc, idesc_s, 0);
-                    tc_mma_ss(t_s + bsel * 64, qdesc + 2, kdesc + 2, idesc_s, 1);
-                    tc_commit(&s_full[bsel]);
-                    if (pre + 1 == n) tc_commit(q_empty);
-                }
-                __syncwarp();
-            }
-            for (int jj = 0; jj < n; ++jj, ++g) {
-                const bool has2 = (jj + 2 < n);
-                const uint32_t vs = (kc + jj) % NST;          // stage of this step (V^T)
-                const uint32_t ks = (kc + jj + 2) % NST;      // stage of step jj + 2 (K)
-                if (has2) mbar_wait_sleep(&kv_full[ks], ((kc + jj + 2) / NST) & 1);
-                const uint32_t bsel = g & 1;
-                const uint64_t vdesc = make_kmajor_desc(s_base + Q_BYTES + vs * STAGE_BYTES + K_BYTES, 128);
-                const uint64_t kdesc = make_kmajor_desc(s_base + Q_BYTES + ks * STAGE_BYTES, 64);
-                if (leader) CMT_TRACE(i, g, 11);
-                mbar_wait_sleep(&p_full[bsel], (g >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    CMT_TRACE(i, g, 4);
-                    const uint32_t t_sp = t_s + bsel * 64;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tc_mma_ts(t_o, t_sp + kk * 8, vdesc + kk * 2, idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
-                    if (jj + 1 == n) tc_commit(o_full);
-                    else tc_commit(pv_done);
-                    if (has2) {
-                        tc_mma_ss(t_sp, qdesc, kdesc, idesc_s, 0);
-                        tc_mma_ss(t_sp, qdesc + 2, kdesc + 2, idesc_s, 1);
-                        tc_commit(&s_full[bsel]);
-                        if (jj + 3 == n) tc_commit(q_empty);
-                    }
-                    tc_commit(&kv_empty[vs]);
-                    CMT_TRACE(i, g, 5);
-                }
-                __syncwarp();
-            }
-            kc += n;
-            pos += n;
-            ++seg;
-        }
-    } else {
-        // --------------------------- softmax warpgroup of slot wg ---------------------------
-        const int wg = warp >> 2;
-        const int r = (warp & 3) * 32 + lane;           // row inside the 128-row tile == TMEM lane
-        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_base + wg * 128;   // + 64 * buffer
-        const uint32_t t_o = tmem_base + lane_base + COL_O + wg * 32;
-        uint64_t* bw = bars + wg * NBAR;
-        uint64_t* s_full = bw + 2 + 2 * NST;
-        uint64_t* p_full = s_full + 2;
-        uint64_t* pv_done = s_full + 4;
-        uint64_t* o_full = s_full + 5;
-        const bool tracer = (threadIdx.x & 127) == 0;
-        (void)tracer;
-        const long long sl = static_cast<long long>(blockIdx.x) * NWG + wg;
-        const long long pos_end = range_start(p, sl + 1, G);
-        uint32_t g = 0, seg = 0, pv_base = 0;   // pv_base: pv_done phases of the earlier segments (n - 1 each)
-        for (long long pos = range_start(p, sl, G); pos < pos_end;) {
-            const Seg sg = decode_seg(p, pos, pos_end);
-            const int n = sg.n, j0 = sg.j0;
-            pos += n;
-            if (sg.qt * QBLK + (warp & 3) * 32 >= p.Nq) {
-                // all 32 rows of this warp are past the last query (the 4-query tail tile: three warps of four):
-                // keep the barrier protocol in step, skip the exponentials
-                for (int jj = 0; jj < n; ++jj, ++g) {
-                    mbar_wait_sleep(&s_full[g & 1], (g >> 1) & 1);
-                    mbar_arrive(&p_full[g & 1]);
-                }
-                mbar_wait_sleep(o_full, seg & 1);
-                ++seg;
-                pv_base += n - 1;
-                continue;
-            }
-            float m = -INFINITY, l = 0.0f;
-            for (int jj = 0; jj < n; ++jj, ++g) {
-                const uint32_t bsel = g & 1;
-                const uint32_t t_sb = t_s + bsel * 64;
-                CMT_S_WAIT(&s_full[bsel], (g >> 1) & 1);
-                if (tracer) CMT_TRACE(wg, g, 0);
-                tc_fence_after();
-                uint32_t s[2][32];
-                tmem_ld32(t_sb + 0, s[0]);
-                tmem_ld32(t_sb + 32, s[1]);
-                tc_wait_ld();
-                if (tracer) CMT_TRACE(wg, g, 1);
-                const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
-                if (valid < KT) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[0][16 + i]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[1][i]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[1][16 + i]));
-                }
-                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (jj == 0) {
-                    m = mx;  // O is overwritten by the first PV of the segment: nothing to rescale
-                } else {
-                    const bool need = (mx - m) > RESCALE_THRESHOLD;
-                    if (__any_sync(0xffffffffu, need)) {
-                        // PV(step - 1) may still be accumulating into O: wait for it before touching O
-                        mbar_wait(pv_done, (pv_base + jj - 1) & 1);
-                        tc_fence_after();
-                        const float m_new = need ? mx : m;
-                        const float alpha = ex2_approx(m - m_new);
-                        l *= alpha;
-                        uint32_t o[32];
-                        tmem_ld32(t_o, o);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(t_o, o);
-                        m = m_new;
-                    }
-                }
-                if (tracer) CMT_TRACE(wg, g, 2);
-                if (tracer) CMT_TRACE(wg, g, 12);
-                // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs
-                const uint64_t neg_m2 = pack_f32x2(-m, -m);
-                uint64_t l2 = pack_f32x2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
-                        float e0, e1;
-                        // one PAIR of exponentials in DB_POLY runs on the FMA pipes (packed cubic) instead of the MUFU
-                        if (DB_POLY > 0 && (i % (DB_POLY > 0 ? DB_POLY : 1)) == DB_POLY - 1) {
-                            ex2_poly_pair(x2, e0, e1);
-                        } else {
-                            float x0, x1;
-                            unpack_f32x2(x2, x0, x1);
-                            e0 = ex2_approx(x0);
-                            e1 = ex2_approx(x1);
-                        }
-                        l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-                        pk[i] = pack_bf16x2(e0, e1);
-                    }
-                    tmem_st16(t_sb + c * 16, pk);
-                }
-                {
-                    float l0, l1;
-                    unpack_f32x2(l2, l0, l1);
-                    l += l0 + l1;
-                }
-                tc_wait_st();
-                if (lane == 0) CMT_TRACE(wg, g, (warp & 3) == 0 ? 3 : 7 + (warp & 3));
-                tc_fence_before();
-                mbar_arrive(&p_full[bsel]);
-            }
-            // segment epilogue: normalised partial + log2-sum-exp into the workspace
-            mbar_wait(o_full, seg & 1);
-            ++seg;
-            pv_base += n - 1;
-            tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(t_o, o);
-            tc_wait_ld();
-            const int slot = sg.item * p.S_max + (static_cast<int>(sl) - cta_of(p, static_cast<long long>(sg.item) * p.T, G));
-            const long long prow = static_cast<long long>(slot) * QBLK + r;
-            const float inv = 1.0f / l;
-            float4* dst = reinterpret_cast<float4*>(p.part_o + prow * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv,
-                                     __uint_as_float(o[4 * i + 2]) * inv, __uint_as_float(o[4 * i + 3]) * inv);
-            p.part_lse[prow] = m + log2f(l);
-            tc_fence_before();
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[3 * TRACE_STEPS * 16 + blockIdx.x] = clock64() - t_start;
-    if (warp == W_TMA) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
 
 // Merge the per-CTA segments of each item.  One thread = (item row, 4 output dims).
 template <bool kBf16>
@@ -966,7 +624,7 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < nseg; ++s) {
             const long long prow = (static_cast<long long>(item) * p.S_max + s) * QB + rr;
-            const float w = exp2f(p.part_lse[prow] - mx);
+            const float w = (mx == -INFINITY) ? 0.f : exp2f(p.part_lse[prow] - mx);   // -inf: no attended key at all
             den += w;
             const float4 x = reinterpret_cast<const float4*>(p.part_o + prow * 32)[q4];
             acc.x = fmaf(w, x.x, acc.x);
@@ -974,7 +632,7 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
             acc.z = fmaf(w, x.z, acc.z);
             acc.w = fmaf(w, x.w, acc.w);
         }
-        const float inv = 1.0f / den;
+        const float inv = den > 0.f ? 1.0f / den : 0.f;
         acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
         const long long oidx = ((static_cast<long long>(b) * p.Nq + row) * p.H + h) * 8 + q4;  // float4 units
         if (kBf16) {
@@ -990,48 +648,23 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
     }
 }
 
-// Kernel variant, read once per process from CMT_ATTN_VARIANT: "iw" (default: three independent warpgroup
-// pipelines, items of 128 queries) or "db" (three warpgroups sharing one K/V stream, items of 384 queries).
-enum AttnVariant { kAttnDb = 0, kAttnIw = 1 };
-static AttnVariant attn_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("CMT_ATTN_VARIANT");
-        v = kAttnDb;
-        if (e != nullptr && strcmp(e, "iw") == 0) v = kAttnIw;
-    }
-    return static_cast<AttnVariant>(v);
-}
-
-#ifndef CMT_ATTN_IW_WFULL
-#define CMT_ATTN_IW_WFULL 5
-#endif
-#ifndef CMT_ATTN_IW_WTAIL
-#define CMT_ATTN_IW_WTAIL 3
-#endif
-
-// Work plan.  G = number of weighted ranges ("slots": CTAs for db, warpgroups for iw); *grid = CTAs.
+// Work plan.  G = number of weighted ranges = CTAs.
+// (An "independent warpgroup" variant -- one K/V stream per warpgroup, items of 128 queries, 3 ranges per CTA -- was
+// built and measured in round 1: parity-green but 1108 vs 973 us.  A 4-query tail tile still loads one SM
+// sub-partition with three active warps, so it costs a full tile; see DESIGN.md.)
 static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid, long long* slots_out) {
-    const AttnVariant var = attn_variant();
-    const int per_cta = var == kAttnIw ? attniw::NWG : 1;
-    p->qblk = var == kAttnIw ? attniw::QBLK : attndb::QBLK;
+    const int per_cta = 1;
+    p->qblk = attndb::QBLK;
     p->kt = attndb::KT;
     p->qblocks = (Nq + p->qblk - 1) / p->qblk;
     p->T = (n_tok + p->kt - 1) / p->kt;
     const long long items = static_cast<long long>(B) * H * p->qblocks;
     p->W = items * p->T;
     const int rows_last = Nq - (p->qblocks - 1) * p->qblk;
-    if (var == kAttnIw) {
-        // step weights (measured): a full tile is MUFU-bound together with its two neighbours; a tile with one or two
-        // active warps is bound by its own chain (TMEM load, max, exponentials, store, barrier round trip)
-        p->w_full = CMT_ATTN_IW_WFULL;
-        p->w_last = rows_last <= 32 ? CMT_ATTN_IW_WTAIL : (rows_last <= 64 ? CMT_ATTN_IW_WFULL - 1 : CMT_ATTN_IW_WFULL);
-    } else {
-        // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
-        // own chain, ~3/4 of that
-        p->w_full = 4;
-        p->w_last = (rows_last + 127) / 128 < attndb::NWG ? 3 : 4;
-    }
+    // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
+    // own chain, ~3/4 of that
+    p->w_full = 4;
+    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? 3 : 4;
     p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
     p->Wtot = static_cast<long long>(B) * H * p->Wg;
     // no more slots than full-weight steps, so that a range is never shorter than the widest step
@@ -1061,7 +694,8 @@ size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     long long G;
     attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid, &G);
     const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
-    return slots * p.qblk * 33 * sizeof(float) + 256;
+    // partials + alignment + the packed key mask (used only when a key_padding_mask is given)
+    return slots * p.qblk * 33 * sizeof(float) + 256 + static_cast<size_t>(B) * p.T * 8 + 8;
 }
 
 int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -1092,13 +726,23 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     p.part_o = reinterpret_cast<float*>(wsp);
     p.part_lse = p.part_o + slots * p.qblk * 32;
     p.trace = g_trace_buf;
+    p.mask_bits = nullptr;
+    if (a.key_keep != nullptr) {
+        uintptr_t mb = (reinterpret_cast<uintptr_t>(p.part_lse + slots * p.qblk) + 7) & ~uintptr_t(7);
+        unsigned long long* bits = reinterpret_cast<unsigned long long*>(mb);
+        const long long n = static_cast<long long>(a.B) * p.T;
+        pack_key_mask_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(a.key_keep, bits, a.B, a.N_kv, a.kv_begin,
+                                                                                a.kv_end, p.T);
+        CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(mask)");
+        p.mask_bits = bits;
+    }
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_attn_iw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attniw::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_iw)");
-        e = cudaFuncSetAttribute(tc_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_attn_db_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
+        e = cudaFuncSetAttribute(tc_attn_db_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db<mask>)");
 
         attr_done = true;
     }
@@ -1125,10 +769,10 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
         int rc = encode_tma_bf16(&tv, a.vt, 4, dims, strides, box, 128);
         if (rc) return rc;
     }
-    if (attn_variant() == kAttnDb)
-        tc_attn_db_kernel<<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    if (p.mask_bits != nullptr)
+        tc_attn_db_kernel<true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     else
-        tc_attn_iw_kernel<<<grid, attniw::THREADS, attniw::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        tc_attn_db_kernel<false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
     const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * p.qblk * 8;
     long long mblocks = (total + 255) / 256;

@@ -226,8 +226,8 @@ size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
 
 int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int H, int Nq,
                        int N_kv, int kv_begin, int kv_end, int64_t q_ld, int64_t k_bstride, int64_t k_hstride,
-                       int64_t v_bstride, int64_t v_hstride, int64_t v_ld, int dtype, int o_dtype,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       int64_t v_bstride, int64_t v_hstride, int64_t v_ld, const unsigned char* key_keep, int dtype,
+                       int o_dtype, void* workspace, size_t workspace_bytes, void* stream) {
     CMT_REQUIRE_DEVICE();
     CMT_CHECK_ARG(q && k && vt && o, "cmt_cross_attn_fwd: null pointer");
     CMT_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && N_kv > 0, "cmt_cross_attn_fwd: bad shape");
@@ -255,6 +255,7 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
     a.v_hstride = v_hstride;
     a.v_ld = v_ld;
     a.o_bf16 = o_dtype == CMT_BF16;
+    a.key_keep = key_keep;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CMT_BF16) return launch_tc_attn(a, workspace, workspace_bytes, s);
     return launch_simt_attn(a, dtype == CMT_BF16_SIMT ? CMT_BF16 : dtype, s);

@@ -26,6 +26,7 @@ struct AttnArgs {
     int B, H, Nq, N_kv, kv_begin, kv_end;
     long long q_ld, k_bstride, k_hstride, v_bstride, v_hstride, v_ld;
     int o_bf16;
+    const unsigned char* key_keep;   // [B, N_kv] 1 = attend, 0 = padded key (attention.py:76-90), or nullptr
 };
 
 // pe_kernels.cu

@@ -121,9 +121,12 @@ __global__ void __launch_bounds__(128) simt_attn_kernel(AttnArgs a) {
                 float acc = 0.0f;
 #pragma unroll
                 for (int d = 0; d < 32; ++d) acc = fmaf(q[d], Ks[c0 + i][d], acc);
-                s[i] = (c0 + i < nt) ? acc : -INFINITY;
+                const bool keep = c0 + i < nt && (a.key_keep == nullptr ||
+                                                  a.key_keep[static_cast<long long>(b) * a.N_kv + t0 + c0 + i] != 0);
+                s[i] = keep ? acc : -INFINITY;
                 cmax = fmaxf(cmax, s[i]);
             }
+            if (cmax == -INFINITY) continue;   // every key of the chunk is padding
             const float m_new = fmaxf(m, cmax);
             const float alpha = (m == -INFINITY) ? 0.0f : exp2f(m - m_new);
             l *= alpha;

@@ -249,9 +249,11 @@ def _workspace(dev, nbytes):
 
 
 def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False,
-               tag="cross_attn"):
+               key_keep=None, tag="cross_attn"):
     """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
-    vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq])."""
+    vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq]).
+    key_keep: optional [B,N_kv] bool/uint8, True = attend (the key_padding_mask of attention.py:76-90, whose
+    unpad_input keeps the True entries)."""
     q = _cuda(q, "q")
     k = _cuda(k, "k", q.dtype)
     vt = _cuda(vt, "vt", q.dtype)
@@ -276,6 +278,10 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         with torch.cuda.device(q.device):
             ws_bytes = int(lib.cmt_cross_attn_workspace_bytes(B, H, Nq, kv_end - kv_begin))
         ws = _workspace(q.device, ws_bytes)
+    if key_keep is not None:
+        key_keep = _cuda(key_keep, "key_keep")
+        assert key_keep.shape == (B, N_kv), f"key_keep must be [B, N_kv] = {(B, N_kv)}, got {tuple(key_keep.shape)}"
+        key_keep = key_keep.to(torch.uint8).contiguous()
     ev = _profile.get(tag)
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -283,12 +289,12 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
     with torch.cuda.device(q.device):
         rc = lib.cmt_cross_attn_fwd(_ptr(q), kp, vp, _ptr(o), _ptr(lse), B, H, Nq, N_kv, kv_begin, kv_end, HD,
                                     L * H * N_kv * HEAD_DIM, N_kv * HEAD_DIM, L * H * HEAD_DIM * ld, HEAD_DIM * ld,
-                                    ld, dt, _dt(o_dtype), _ptr(ws), ws_bytes, _stream(q))
+                                    ld, _ptr(key_keep), dt, _dt(o_dtype), _ptr(ws), ws_bytes, _stream(q))
     if ev is not None:
         e1.record()
         ev.append((e0, e1))
     _lib.check(rc, "cmt_cross_attn_fwd")
-    _count(2 if dt == CMT_BF16 else 1)
+    _count((2 if dt == CMT_BF16 else 1) + (1 if key_keep is not None and dt == CMT_BF16 else 0))
     return (o, lse) if return_lse else o
 
 

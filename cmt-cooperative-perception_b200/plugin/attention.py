@@ -53,8 +53,9 @@ class FlashAttention(nn.Module):
         if causal:
             raise NotImplementedError("causal attention is never used on the CMT path (attention.py:98)")
         if key_padding_mask is not None:
-            raise NotImplementedError("key_padding_mask: the reference always passes None "
-                                      "(petr_transformer.py:312-316)")
+            # attention.py:76-90: unpad_input keeps the keys whose mask entry is True (flash-attn bert_padding
+            # convention) and packs them with cu_seqlens_k; masking the dropped keys is the same softmax
+            assert key_padding_mask.shape == (q.shape[0], kv.shape[1]), "key_padding_mask must be [B, S]"
         if self.training and self.dropout_p > 0:
             raise NotImplementedError("forward/inference only")
         B, T, H, D = q.shape
@@ -67,7 +68,8 @@ class FlashAttention(nn.Module):
         ld = (S + 7) // 8 * 8
         vt = torch.zeros((B, 1, H, D, ld), dtype=dt, device=q.device)
         vt[..., :S] = kv[:, :, 1].permute(0, 2, 3, 1).to(dt)
-        o = ops.cross_attn(qs, k, vt, 0, o_dtype=torch.float32)
+        o = ops.cross_attn(qs, k, vt, 0, o_dtype=torch.float32,
+                           key_keep=None if key_padding_mask is None else key_padding_mask.to(q.device).bool())
         return o.view(B, T, H, D), None
 
 
@@ -128,10 +130,11 @@ class FlashMHA(nn.Module):
         dt = _compute_dtype(self.precision)
         return ops.linear(q.to(dt).contiguous(), ws["wq"], ws["bq"], alpha=_Q_SCALE, out_dtype=dt)
 
-    def attend(self, q, cache: KVCache, layer: int, kv_begin=0, kv_end=None, return_lse=False, o_dtype=None):
+    def attend(self, q, cache: KVCache, layer: int, kv_begin=0, kv_end=None, return_lse=False, o_dtype=None,
+               key_keep=None):
         qp = self.project_q(q)
         return ops.cross_attn(qp, cache.k, cache.vt, layer, kv_begin=kv_begin, kv_end=kv_end,
-                              return_lse=return_lse, o_dtype=o_dtype)
+                              return_lse=return_lse, o_dtype=o_dtype, key_keep=key_keep)
 
     def project_out(self, ctx):
         ws = self.compute_weights()
@@ -142,8 +145,13 @@ class FlashMHA(nn.Module):
         taken from the hoisted all-layer projection and `k`/`v` are ignored."""
         if self.training:
             raise NotImplementedError("libcmtcoop_b200 is forward/inference only")
+        key_keep = None
         if key_padding_mask is not None:
-            raise NotImplementedError("key_padding_mask is always None on the CMT path (petr_transformer.py:312-316)")
+            # attention.py:131-137 hands the mask to FlashAttention, whose unpad_input keeps the True entries
+            # (attention.py:76-90); the CMT wrappers always pass None (petr_transformer.py:312-316)
+            if kv_cache is not None and kv_cache.group is not None:
+                raise NotImplementedError("key_padding_mask together with the multi-GPU KV-token split")
+            key_keep = key_padding_mask.to(q.device).bool()
         if not q.is_cuda:
             raise RuntimeError("FlashMHA needs CUDA tensors: libcmtcoop_b200 has no CPU fallback")
         if kv_cache is None:
@@ -153,7 +161,7 @@ class FlashMHA(nn.Module):
             vt = ops.project_values_t(v.to(dt).contiguous(), ws["wv"], ws["bv"], 1, self.num_heads)
             kv_cache, layer_index = KVCache(kk, vt, k.shape[1]), 0
         if kv_cache.group is None:
-            ctx = self.attend(q, kv_cache, layer_index)
+            ctx = self.attend(q, kv_cache, layer_index, key_keep=key_keep)
         else:
             ctx = self._attend_kv_split(q, kv_cache, layer_index)
         return self.project_out(ctx), None

@@ -113,6 +113,9 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
  * vt:  per (b,h) a [32,N_kv] matrix (row stride v_ld) at vt + b*v_bstride + h*v_hstride
  * Only tokens [kv_begin,kv_end) are attended (multi-GPU / split-KV partials).
  * o:   [B,Nq,H*32] (o_dtype, row stride H*32), normalised over the attended tokens
+ * key_keep: [B,N_kv] bytes, 1 = attend, 0 = padded key, or NULL.  This is the key_padding_mask branch of
+ *      FlashAttention.forward (attention.py:76-90: unpad_input + cu_seqlens_k); dropping a key from the packed
+ *      sequence and giving it weight zero are the same softmax.  A query with no attended key gets o = 0.
  * lse: [B,H,Nq] fp32 natural-log sum-exp of the scaled scores over the attended tokens, or NULL
  * dtype bf16 -> tcgen05 kernel, work split over all SMs along the KV axis with partials in
  * `workspace` (cmt_cross_attn_workspace_bytes) merged by a second kernel; dtype fp32 -> fp32
@@ -121,8 +124,8 @@ size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens);
 int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B,
                        int H, int Nq, int N_kv, int kv_begin, int kv_end, int64_t q_ld,
                        int64_t k_bstride, int64_t k_hstride, int64_t v_bstride, int64_t v_hstride,
-                       int64_t v_ld, int dtype, int o_dtype, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       int64_t v_ld, const unsigned char* key_keep, int dtype, int o_dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Log-sum-exp merge of G partial attention results (KV-token split across GPUs or streams):
  * o_parts [G,B,Nq,H*32] fp32, lse_parts [G,B,H,Nq] fp32 (natural log) -> o [B,Nq,H*32], lse. */

@@ -123,10 +123,14 @@ def rv_query_feats(ref, lidar2img, img2lidar, depth_num, pad_h, pad_w, pc_range)
 # ---------------------------------------------------------------------------------------------
 # attention / decoder
 # ---------------------------------------------------------------------------------------------
-def mha(query, key, value, sd, prefix, num_heads=8, head_chunk=2):
+def mha(query, key, value, sd, prefix, num_heads=8, head_chunk=2, key_keep=None):
     """nn.MultiheadAttention forward (the CPU/fp32 cross-attention oracle path,
     models/utils/petr_transformer.py:37-177 wraps it; same parameter names as FlashMHA,
-    models/utils/attention.py:95-138).  query [Nq,B,C], key/value [Nk,B,C] seq-first."""
+    models/utils/attention.py:95-138).  query [Nq,B,C], key/value [Nk,B,C] seq-first.
+    key_keep [B,Nk] bool: the key_padding_mask branch of FlashAttention.forward (attention.py:76-90).  There the
+    mask goes to flash_attn.bert_padding.unpad_input (flash-attn 0.2.2, not under /root/reference: it keeps the
+    entries where the mask is True -- `indices = nonzero(mask.flatten())` -- and builds cu_seqlens_k from the
+    per-frame counts), so a False key simply does not exist for its frame: weight zero here."""
     w = sd[prefix + ".in_proj_weight"]
     b = sd[prefix + ".in_proj_bias"]
     C = query.shape[-1]
@@ -143,6 +147,8 @@ def mha(query, key, value, sd, prefix, num_heads=8, head_chunk=2):
     scale = 1.0 / math.sqrt(d)
     for h0 in range(0, num_heads, head_chunk):  # bounded memory for 900 x 56400 score maps
         s = torch.matmul(q[:, h0:h0 + head_chunk] * scale, k[:, h0:h0 + head_chunk].transpose(-1, -2))
+        if key_keep is not None:
+            s = s.masked_fill(~key_keep.bool()[:, None, None, :], float("-inf"))
         p = torch.softmax(s, dim=-1)
         out[:, h0:h0 + head_chunk] = torch.matmul(p, v[:, h0:h0 + head_chunk])
     out = out.permute(2, 0, 1, 3).reshape(Nq, B, C)

@@ -60,3 +60,26 @@ def test_fused_decoder_equals_module_path(kind, precision, tol):
     assert n_fused > n_mod                                  # the small ops moved into the library
     for name in fused[0]:
         assert O.rel_l2(fused[0][name].float().cpu(), modular[0][name].float().cpu()) < tol, name
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_flash_mha_key_padding_mask(precision, tol):
+    """FlashMHA.forward(q, k, v, key_padding_mask) (attention.py:126-138 -> :76-90) against the oracle's
+    nn.MultiheadAttention math with the padded keys dropped."""
+    from cmtcoop_b200.plugin.attention import FlashMHA
+    g = torch.Generator().manual_seed(3)
+    B, Nq, S, E, H = 2, 50, 333, 256, 8
+    mha = FlashMHA(E, H).eval()
+    with torch.no_grad():
+        for p in mha.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    sd = {"a." + k: v.detach().clone() for k, v in mha.state_dict().items()}
+    mha = mha.to(DEV)
+    mha.precision = precision
+    q, k, v = (torch.randn(B, n, E, generator=g) for n in (Nq, S, S))
+    keep = torch.rand(B, S, generator=g) > 0.35
+    keep[0, :130] = False
+    with torch.no_grad():
+        out, _ = mha(q.to(DEV), k.to(DEV), v.to(DEV), key_padding_mask=keep.to(DEV))
+    want = O.mha(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), sd, "a", num_heads=H, key_keep=keep).transpose(0, 1)
+    assert O.rel_l2(out.cpu(), want) < tol

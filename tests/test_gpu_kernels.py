@@ -227,3 +227,39 @@ def test_cross_attention_matches_simt_on_same_bf16_inputs():
     a = ops.cross_attn(q, k, vt, 0, o_dtype=torch.float32)
     b = ops.cross_attn(q, k, vt, 0, o_dtype=torch.float32, simt=True)
     assert _rel(a, b) < 6e-3
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tcgen05"])
+def test_cross_attention_key_padding_mask(mode):
+    """key_padding_mask branch (attention.py:76-90): padded keys carry no weight.  Frame 0: random padding; frame 1:
+    the first 200 keys (three whole 64-key tiles) padded, so stream-K segments start on fully padded tiles; frame 2:
+    valid prefix only (the usual var-len case)."""
+    B, H, Nq, N_kv = 3, 8, 200, 1500
+    g = torch.Generator().manual_seed(17)
+    dt = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    q = (torch.randn(B, Nq, H * 32, generator=g) * (ops.LOG2E / math.sqrt(32)) * 2.0).to(dt)
+    k = torch.randn(B, 1, H, N_kv, 32, generator=g).to(dt)
+    ld = (N_kv + 7) // 8 * 8
+    vt = torch.zeros(B, 1, H, 32, ld)
+    vt[..., :N_kv] = torch.randn(B, 1, H, 32, N_kv, generator=g)
+    vt = vt.to(dt)
+    keep = torch.rand(B, N_kv, generator=g) > 0.3
+    keep[1, :200] = False
+    keep[2] = torch.arange(N_kv) < 777
+    qh = q.double().view(B, Nq, H, 32).permute(0, 2, 1, 3)
+    s = qh @ k.double()[:, 0].transpose(-1, -2) * math.log(2.0)
+    s = s.masked_fill(~keep[:, None, None, :], float("-inf"))
+    want = (torch.softmax(s, -1) @ vt.double()[:, 0, :, :, :N_kv].transpose(-1, -2)).permute(0, 2, 1, 3).reshape(B, Nq, H * 32)
+    want_lse = torch.logsumexp(s, -1)
+    o, lse = ops.cross_attn(q.to(DEV), k.to(DEV), vt.to(DEV), 0, o_dtype=torch.float32, return_lse=True,
+                            key_keep=keep.to(DEV))
+    torch.cuda.synchronize()
+    tol = 2e-5 if mode == "simt_fp32" else 4e-3
+    assert _rel(o, want) < tol, _rel(o, want)
+    assert (lse.cpu() - want_lse).abs().max() < (1e-4 if mode == "simt_fp32" else 4e-3)
+    # and it is exactly the attention over the gathered keys (what unpad_input + cu_seqlens_k computes)
+    idx = keep[2].nonzero().flatten()
+    o2 = ops.cross_attn(q[2:3].to(DEV), k[2:3, :, :, idx].contiguous().to(DEV),
+                        torch.nn.functional.pad(vt[2:3, ..., idx], (0, (-len(idx)) % 8)).contiguous().to(DEV), 0,
+                        o_dtype=torch.float32)
+    assert _rel(o[2:3], o2.cpu()) < tol

@@ -47,3 +47,26 @@ def test_oracle_matches_reference_golden(kind, golden_dir):
         # top-k over near-tied scores of an untrained decoder is order-unstable:
         # compare the box SETS, tolerating a few swaps at the k-th score boundary.
         assert O.box_set_overlap(b["bboxes"], torch.from_numpy(gold[f"boxes{i}.bboxes"]), 1e-3) >= 0.9
+
+
+def test_oracle_mha_key_padding_equals_unpadded_keys():
+    """attention.py:76-90: with a key_padding_mask the reference gathers the kept keys of every frame
+    (unpad_input) and attends over the packed sequence.  The oracle's masked form must equal attention over the
+    explicitly gathered keys, frame by frame."""
+    import torch
+    from oracle import cmt_oracle as O
+    g = torch.Generator().manual_seed(5)
+    C, H, Nq, Nk, B = 64, 8, 7, 37, 3
+    sd = {"a.in_proj_weight": torch.randn(3 * C, C, generator=g) * 0.2, "a.in_proj_bias": torch.randn(3 * C, generator=g) * 0.1,
+          "a.out_proj.weight": torch.randn(C, C, generator=g) * 0.2, "a.out_proj.bias": torch.randn(C, generator=g) * 0.1}
+    q = torch.randn(Nq, B, C, generator=g)
+    k = torch.randn(Nk, B, C, generator=g)
+    v = torch.randn(Nk, B, C, generator=g)
+    keep = torch.rand(B, Nk, generator=g) > 0.4
+    keep[1, :20] = False           # a long padded prefix
+    keep[2] = True                 # one frame without padding
+    got = O.mha(q, k, v, sd, "a", num_heads=H, key_keep=keep)
+    for b in range(B):
+        idx = keep[b].nonzero().flatten()
+        want = O.mha(q[:, b:b + 1], k[idx][:, b:b + 1], v[idx][:, b:b + 1], sd, "a", num_heads=H)
+        assert torch.allclose(got[:, b:b + 1], want, atol=1e-5, rtol=1e-5)
