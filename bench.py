@@ -13,7 +13,7 @@ d=256, bf16), 8 frames per GPU; frames shard across GPUs with no data-path colle
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
 `e2e` = the same forward through the public head API from pinned HOST buffers (H2D + D2H in the timed
-region); `roofline` is for the dominant kernel (tc_attn_kernel); `cpu_baseline` is the CPU oracle on a
+region); `roofline` is for the dominant kernel (tc_attn_db_kernel); `cpu_baseline` is the CPU oracle on a
 bounded sample.  Only the cpu_baseline / --impl reference legs touch oracle/.
 """
 import argparse
@@ -45,10 +45,10 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of tc_attn_kernel per launch from the committed ncu --set full
-# capture (profiles/r1_attn_gemm_ncu_raw.csv: 1.8615 GB + 0.0139 GB at B=8), per frame.  K+V of one layer are
-# 57.8 MB per frame; the 4 query blocks of a (frame, head) stream them at different times, hence 4.06x.
-NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.861532e9 + 0.013930e9) / 8}
+# dram__bytes_read.sum + dram__bytes_write.sum of tc_attn_db_kernel per launch from the committed ncu --set full
+# capture (profiles/r1_attn_db_n3s_ncu_raw.csv: 1.3963 GB + 0.0113 GB at B=8), per frame.  K+V of one layer are
+# 57.8 MB per frame; the 3 query blocks of a (frame, head) stream them at different times, hence ~3x.
+NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.396296e9 + 0.011308e9) / 8}
 
 
 def build_case(workload, B, seed=0):
@@ -292,7 +292,7 @@ def main():
     roof = None
     if attn_avg_ms:
         achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="tc_attn_kernel(+merge)", achieved=achieved,
+        roof = dict(bound="tensor", kernel="tc_attn_db_kernel(+merge)", achieved=achieved,
                     peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"],
                     traffic=NCU_DRAM_BYTES_PER_FRAME.get(args.workload, 0) * B or None, peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
                     launches_timed=len(attn_ms), avg_launch_ms=attn_avg_ms,
