@@ -16,6 +16,7 @@
 // than 2^8, so the common tile does no accumulator traffic at all.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -77,6 +78,11 @@ struct TcAttnParams {
     // key padding mask (attention.py:76-90): bit i of mask_bits[b * T + j] = key kv_begin + 64 j + i of frame b is
     // attended (and < kv_end); nullptr = no mask.  Packed from the byte mask by pack_key_mask_kernel.
     const unsigned long long* mask_bits;
+    // static softmax shift: max |q|^2 per (frame, head) [B*H] and max |k|^2 per (frame, head) at
+    // k_norm2[b * kn_bstride + h] (written by the projection GEMMs' epilogues); nullptr = online softmax everywhere
+    const float* q_norm2;
+    const float* k_norm2;
+    long long kn_bstride;
     long long* trace; // debug: clock64 event trace of CTA 0 (three-warpgroup kernel), nullptr = off
 };
 constexpr int TRACE_STEPS = 96;
@@ -170,9 +176,6 @@ constexpr int KV_BYTES = 64 * 32 * 2;   // 4 KB per K tile / V^T tile
 #ifndef CMT_ISSUER_WAIT
 #define CMT_ISSUER_WAIT mbar_wait_sleep
 #endif
-#ifndef CMT_TOK_WAIT
-#define CMT_TOK_WAIT mbar_wait_sleep      // softmax warps: MUFU token
-#endif
 #ifndef CMT_S_WAIT
 #define CMT_S_WAIT mbar_wait              // softmax warps: scores ready
 #endif
@@ -194,29 +197,20 @@ constexpr float RESCALE_THRESHOLD = 8.0f;
 // With the scores double-buffered and the packed FADD2 softmax, the steady-state step sits within ~7 % of the
 // MUFU bound (16 ex2 / clk / SM), so moving exponentials to the FMA pipes pays: pairs i with i % DB_POLY ==
 // DB_POLY - 1 of every 16-pair chunk use the packed cubic (ex2_poly_pair).  Measured (B=8, 56 400 tokens, same
-// box): off 1100 us, 1/16 1110, 1/8 1056, 1/6 1029, 1/5 1077, 1/4 1106, 1/3 1140, 1/2 1190.
+// box): off 1100 us, 1/16 1110, 1/8 1056, 1/6 1029, 1/5 1077, 1/4 1106, 1/3 1140, 1/2 1190; with the three sleeping
+// issuers (below): off 1041, i%8 969, i%6 958, i%5 946 (shipped: 6 of 32 pairs), i%4 976, i%3 1033.
 #ifndef CMT_ATTN_DB_POLY
-#define CMT_ATTN_DB_POLY 6
+#define CMT_ATTN_DB_POLY 5
 #endif
 constexpr int DB_POLY = CMT_ATTN_DB_POLY;
-// MUFU token ring.  The three softmax warps that share an SM sub-partition (warp w of every warpgroup) contend for
-// its 4-lane MUFU pipe; left alone they fall into a convoy: all three exponentiate together at a third of the rate,
-// finish together, and then all three sit in their MUFU-free phases (TMEM load, row max, P store, barrier round
-// trips) with the pipe idle.  A token per sub-partition serialises the exponential phases instead: warpgroup i
-// waits for its token, exponentiates at full rate and hands the token to warpgroup i+1 after RING_REL of its 32
-// pairs, so the successor's wake-up overlaps the tail and the other two warps' MUFU-free phases hide under it.
-// No token is ever held across a blocking wait, idle warpgroups / all-padding warps just pass it on.
-// Measured: 1058 -> 1015 us with one polling issuer, 992 -> 979 with three, 983 -> 986 with three sleeping issuers
-// (the shipped configuration): the convoy is not what limits the kernel once the issuers are out of the way, and the
-// SM clock under this kernel is ~1.6 GHz (power), so a step is already within ~10 % of the MUFU floor.  Off by default.
-#ifndef CMT_ATTN_RING
-#define CMT_ATTN_RING 0
+// Static softmax shift (see the softmax warps below): items whose Cauchy-Schwarz score bound is at most STATIC_LIMIT
+// skip the row maximum and the rescale machinery; their freed ALU / issue slots take more polynomial exponentials.
+// Measured with a fixed shift (B=8, 56 400 tokens): online i%5 946 us; static i%5 896, i%4 892, i%3 865.
+#ifndef CMT_ATTN_ST_POLY
+#define CMT_ATTN_ST_POLY 3
 #endif
-#ifndef CMT_ATTN_RING_REL
-#define CMT_ATTN_RING_REL 22
-#endif
-constexpr bool RING = CMT_ATTN_RING != 0;
-constexpr int RING_REL = CMT_ATTN_RING_REL;
+constexpr int ST_POLY = CMT_ATTN_ST_POLY;
+constexpr float STATIC_LIMIT = 60.0f;
 }  // namespace attndb
 
 // kMask: key padding mask variant (the unmasked instantiation carries none of its code: even an untaken mask
@@ -239,8 +233,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     uint64_t* p_full = s_full + 2 * NWG;     // [NWG][2]
     uint64_t* pv_done = p_full + 2 * NWG;    // [NWG]
     uint64_t* o_full = pv_done + NWG;        // [NWG]
-    uint64_t* tok = o_full + NWG;            // [NWG][4] MUFU tokens: (warpgroup, warp of the warpgroup)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 4 * NWG);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NWG);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
@@ -266,9 +259,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             mbar_init(&pv_done[i], 1);
             mbar_init(&o_full[i], 1);
         }
-        for (int i = 0; i < 4 * NWG; ++i) mbar_init(&tok[i], 1);
         fence_barrier_init();
-        for (int w = 0; w < 4; ++w) mbar_arrive(&tok[w]);   // warpgroup 0 owns the tokens first
     }
     if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -429,9 +420,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         uint64_t* my_s_full = s_full + 2 * wg;
         uint64_t* my_p_full = p_full + 2 * wg;
         const bool tracer = (threadIdx.x & 127) == 0;
-        uint64_t* my_tok = tok + wg * 4 + (warp & 3);
-        uint64_t* next_tok = tok + ((wg + 1) % NWG) * 4 + (warp & 3);
-        uint32_t turn = 0;                      // steps seen by this warp == token phases consumed
+        (void)tracer;
         uint32_t g = 0, seg = 0, pv_base = 0;   // pv_base: pv_done phases of the earlier segments (n - 1 each)
         for (long long pos = pos_begin; pos < pos_end;) {
             const int item = static_cast<int>(pos / p.T);
@@ -439,24 +428,11 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
             const int qb = item % p.qblocks;
             pos += n;
-            if (qb * QBLK + wg * 128 >= p.Nq) {             // this warpgroup's tile is past the last query
-                if (RING) {
-                    for (int jj = 0; jj < n; ++jj, ++turn) {
-                        CMT_TOK_WAIT(my_tok, turn & 1);
-                        if (lane == 0) mbar_arrive(next_tok);
-                    }
-                }
-                continue;
-            }
+            if (qb * QBLK + wg * 128 >= p.Nq) continue;     // this warpgroup's tile is past the last query
             if (qb * QBLK + wg * 128 + (warp & 3) * 32 >= p.Nq) {
                 // all 32 rows of this warp are past the last query (900 queries: three warps of the eighth tile):
                 // keep the barrier protocol in step, skip the exponentials -- the MUFU pipe is the bound
                 for (int jj = 0; jj < n; ++jj, ++g) {
-                    if (RING) {
-                        CMT_TOK_WAIT(my_tok, turn & 1);
-                        if (lane == 0) mbar_arrive(next_tok);
-                        ++turn;
-                    }
                     mbar_wait(&my_s_full[g & 1], (g >> 1) & 1);
                     mbar_arrive(&my_p_full[g & 1]);
                 }
@@ -465,9 +441,14 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 pv_base += n - 1;
                 continue;
             }
+            const int hb = item / p.qblocks;                // b * H + h
+            const unsigned long long* mask_row = kMask ? p.mask_bits + static_cast<long long>(hb / p.H) * p.T : nullptr;
             float m = -INFINITY, l = 0.0f;
-            const unsigned long long* mask_row = kMask ? p.mask_bits + static_cast<long long>(item / (p.qblocks * p.H)) * p.T : nullptr;
-            for (int jj = 0; jj < n; ++jj, ++g) {
+
+            // One KV step of this thread's row.  kStatic: the softmax shift m is the item's Cauchy-Schwarz score bound
+            // (no row maximum, no rescale of O); otherwise the online form with lazy rescale.
+            auto step = [&](auto static_tag, int jj) {
+                constexpr bool kStatic = decltype(static_tag)::value;
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
                 CMT_S_WAIT(&my_s_full[bsel], (g >> 1) & 1);
@@ -495,44 +476,44 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                         for (int i = 0; i < 32; ++i)
                             if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                if (!kStatic) {
+                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[0][16 + i]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[1][i]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[1][16 + i]));
-                }
-                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (jj == 0) {
-                    // O_i is overwritten by the first PV of the segment: nothing to rescale.  A first tile whose keys
-                    // are all padding has mx = -inf: keep m finite so that x - m stays -inf (weight 0), never NaN.
-                    m = kMask ? fmaxf(mx, -1e30f) : mx;
-                } else {
-                    const bool need = (mx - m) > RESCALE_THRESHOLD;
-                    if (__any_sync(0xffffffffu, need)) {
-                        // PV(step - 1) may still be accumulating into O_i: wait for it before touching O_i
-                        mbar_wait(&pv_done[wg], (pv_base + jj - 1) & 1);
-                        tc_fence_after();
-                        const float m_new = need ? mx : m;
-                        const float alpha = ex2_approx(m - m_new);
-                        l *= alpha;
-                        uint32_t o[32];
-                        tmem_ld32(t_o, o);
-                        tc_wait_ld();
+                    for (int i = 0; i < 16; ++i) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[0][16 + i]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[1][i]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[1][16 + i]));
+                    }
+                    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                    if (jj == 0) {
+                        // O_i is overwritten by the first PV of the segment: nothing to rescale.  A first tile whose
+                        // keys are all padding has mx = -inf: keep m finite so that x - m stays -inf (weight 0).
+                        m = kMask ? fmaxf(mx, -1e30f) : mx;
+                    } else {
+                        const bool need = (mx - m) > RESCALE_THRESHOLD;
+                        if (__any_sync(0xffffffffu, need)) {
+                            // PV(step - 1) may still be accumulating into O_i: wait for it before touching O_i
+                            mbar_wait(&pv_done[wg], (pv_base + jj - 1) & 1);
+                            tc_fence_after();
+                            const float m_new = need ? mx : m;
+                            const float alpha = ex2_approx(m - m_new);
+                            l *= alpha;
+                            uint32_t o[32];
+                            tmem_ld32(t_o, o);
+                            tc_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(t_o, o);
-                        m = m_new;
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(t_o, o);
+                            m = m_new;
+                        }
                     }
                 }
                 if (tracer) CMT_TRACE(wg, g, 2);
-                if (RING) {
-                    CMT_TOK_WAIT(my_tok, turn & 1);
-                    ++turn;
-                }
-                if (tracer) CMT_TRACE(wg, g, 12);
-                // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs
+                // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs.
+                // One PAIR of exponentials in POLY runs on the FMA pipes (packed cubic) instead of the MUFU; without
+                // the row-max work there are issue slots for more of them.
+                constexpr int POLY = kStatic ? ST_POLY : DB_POLY;
                 const uint64_t neg_m2 = pack_f32x2(-m, -m);
                 uint64_t l2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
@@ -540,11 +521,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if (RING && c * 16 + i == RING_REL && lane == 0) mbar_arrive(next_tok);
                         const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
                         float e0, e1;
-                        // one PAIR of exponentials in DB_POLY runs on the FMA pipes (packed cubic) instead of the MUFU
-                        if (DB_POLY > 0 && (i % (DB_POLY > 0 ? DB_POLY : 1)) == DB_POLY - 1) {
+                        if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) {
                             ex2_poly_pair(x2, e0, e1);
                         } else {
                             float x0, x1;
@@ -566,6 +545,22 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 if (lane == 0) CMT_TRACE(wg, g, (warp & 3) == 0 ? 3 : 7 + (warp & 3));
                 tc_fence_before();
                 mbar_arrive(&my_p_full[bsel]);
+                ++g;
+            };
+
+            // static bound of every score of the item: |q . k| <= |q| |k| over the bf16-rounded operands the MMAs see
+            // (the norms come from the fp32 projection outputs: + 2^-7 covers the two roundings).  Scores then lie in
+            // [-m, m], so with m <= STATIC_LIMIT every weight 2^(s - m) stays a normal number.
+            bool stat = false;
+            if (p.q_norm2 != nullptr) {
+                const float bound = sqrtf(__ldg(p.q_norm2 + hb) * __ldg(p.k_norm2 + static_cast<long long>(hb / p.H) * p.kn_bstride + hb % p.H)) * 1.0079f + 1e-3f;
+                stat = bound <= STATIC_LIMIT;
+                if (stat) m = bound;
+            }
+            if (stat) {
+                for (int jj = 0; jj < n; ++jj) step(std::true_type{}, jj);
+            } else {
+                for (int jj = 0; jj < n; ++jj) step(std::false_type{}, jj);
             }
             // segment epilogue: normalised partial + log2-sum-exp into the workspace
             mbar_wait(&o_full[wg], seg & 1);
@@ -726,6 +721,9 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     p.part_o = reinterpret_cast<float*>(wsp);
     p.part_lse = p.part_o + slots * p.qblk * 32;
     p.trace = g_trace_buf;
+    p.q_norm2 = (a.q_norm2 != nullptr && a.k_norm2 != nullptr) ? a.q_norm2 : nullptr;
+    p.k_norm2 = a.k_norm2;
+    p.kn_bstride = a.kn_bstride;
     p.mask_bits = nullptr;
     if (a.key_keep != nullptr) {
         uintptr_t mb = (reinterpret_cast<uintptr_t>(p.part_lse + slots * p.qblk) + 7) & ~uintptr_t(7);

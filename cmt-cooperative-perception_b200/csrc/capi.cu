@@ -184,7 +184,7 @@ int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_p
 int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                       int64_t lda, int64_t ldb, int64_t ldc, int64_t cb, int64_t cb_stride, int batch,
                       int64_t strideA, int64_t strideB, int64_t strideC, float alpha, int flags, int in_dtype,
-                      int out_dtype, void* stream) {
+                      int out_dtype, float* norm2_max, void* stream) {
     CMT_REQUIRE_DEVICE();
     CMT_CHECK_ARG(A && B && C, "cmt_gemm_bias_act: null pointer");
     CMT_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "cmt_gemm_bias_act: bad shape M=%d N=%d K=%d batch=%d", M,
@@ -213,6 +213,9 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
     g.bias_per_row = (flags & CMT_GEMM_BIAS_PER_ROW) ? 1 : 0;
     g.out_bf16 = out_dtype == CMT_BF16;
     g.transpose_c = (flags & CMT_GEMM_TRANSPOSE_OUT) ? 1 : 0;
+    g.norm2_max = norm2_max;
+    CMT_CHECK_ARG(norm2_max == nullptr || (in_dtype == CMT_BF16 && !(flags & CMT_GEMM_FORCE_SIMT)),
+                  "cmt_gemm_bias_act: norm2_max is a bf16 tensor-core path option");
     CMT_CHECK_ARG(!g.transpose_c || (in_dtype == CMT_BF16 && !(flags & CMT_GEMM_FORCE_SIMT)),
                   "cmt_gemm_bias_act: CMT_GEMM_TRANSPOSE_OUT is a bf16 tensor-core path option");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -226,7 +229,8 @@ size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
 
 int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B, int H, int Nq,
                        int N_kv, int kv_begin, int kv_end, int64_t q_ld, int64_t k_bstride, int64_t k_hstride,
-                       int64_t v_bstride, int64_t v_hstride, int64_t v_ld, const unsigned char* key_keep, int dtype,
+                       int64_t v_bstride, int64_t v_hstride, int64_t v_ld, const unsigned char* key_keep,
+                       const float* q_norm2_max, const float* k_norm2_max, int64_t kn_bstride, int dtype,
                        int o_dtype, void* workspace, size_t workspace_bytes, void* stream) {
     CMT_REQUIRE_DEVICE();
     CMT_CHECK_ARG(q && k && vt && o, "cmt_cross_attn_fwd: null pointer");
@@ -256,6 +260,9 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
     a.v_ld = v_ld;
     a.o_bf16 = o_dtype == CMT_BF16;
     a.key_keep = key_keep;
+    a.q_norm2 = q_norm2_max;
+    a.k_norm2 = k_norm2_max;
+    a.kn_bstride = kn_bstride;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CMT_BF16) return launch_tc_attn(a, workspace, workspace_bytes, s);
     return launch_simt_attn(a, dtype == CMT_BF16_SIMT ? CMT_BF16 : dtype, s);

@@ -61,6 +61,7 @@ struct TcGemmParams {
     int a_batched, b_batched;
     int m_tiles, n_tiles, total_tiles, num_kb;
     int direct;     // 1: lean epilogue, 256-bit stores straight from registers (alignment / bias conditions hold)
+    float* norm2_max; // [batch][N/32]: atomicMax of the squared norm of every row's 32-column block (attention score bound), or nullptr
     int transpose_c; // 1: element (m, n) of batch z is stored at z*strideC + (n / cb)*cb_stride + (n % cb)*ldc + m (bf16)
     int b_resident; // 1: gridDim.x = Gm * n_tiles, CTA c owns n-tile c % n_tiles and the (batch, m-tile) pairs c / n_tiles + i * Gm
 };
@@ -292,6 +293,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
                     }
+                    if (p.norm2_max != nullptr) {
+                        // max over the tile's rows of |row block|^2 (non-negative floats order like their bit patterns)
+                        float n2 = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) n2 = fmaf(f[i], f[i], n2);
+                        const unsigned int wmax = __reduce_max_sync(0xffffffffu, m_ok ? __float_as_uint(n2) : 0u);
+                        if (lane == 0)
+                            atomicMax(reinterpret_cast<unsigned int*>(p.norm2_max) + static_cast<long long>(z) * (p.N >> 5) + (n0 >> 5), wmax);
+                    }
                     const long long blk_off = nb * p.cb_stride;
                     if (p.transpose_c) {
                         // element (m, n) -> blk_off + (n % cb) * ldc + m  (bf16 only)
@@ -518,6 +528,7 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
 
     TcGemmParams p{};
     p.transpose_c = g.transpose_c;
+    p.norm2_max = g.norm2_max;
     static const bool no_direct = getenv("CMT_GEMM_NO_DIRECT") != nullptr;
     const bool bias_ok = g.bias == nullptr || g.bias_per_row || g.N <= BIAS_CAP - 64;
     if (g.transpose_c) {
@@ -530,6 +541,8 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
                              (batch == 1 || (g.strideC * esz) % 32 == 0);
         p.direct = (aligned && g.N % 32 == 0 && bias_ok && !no_direct) ? 1 : 0;
     }
+    CMT_CHECK_ARG(g.norm2_max == nullptr || p.direct, "cmt_gemm_bias_act(bf16): norm2_max needs N %% 32 == 0, 32-byte aligned C rows "
+                                                      "and N <= %d with a column bias", BIAS_CAP - 64);
     p.bias = g.bias;
     p.C = g.C;
     p.M = g.M;

@@ -15,6 +15,7 @@ struct GemmArgs {
     float alpha;
     int relu, bias_per_row, out_bf16;
     int transpose_c;   // bf16 tensor-core path only: store C^T inside each column block (see cmt_gemm_bias_act)
+    float* norm2_max;  // bf16 tensor-core path only: [batch][N/32] running max of the squared row norms per 32-column block, or nullptr
 };
 
 struct AttnArgs {
@@ -27,6 +28,9 @@ struct AttnArgs {
     long long q_ld, k_bstride, k_hstride, v_bstride, v_hstride, v_ld;
     int o_bf16;
     const unsigned char* key_keep;   // [B, N_kv] 1 = attend, 0 = padded key (attention.py:76-90), or nullptr
+    const float* q_norm2;            // [B*H] max |q|^2 per (frame, head), or nullptr (online softmax)
+    const float* k_norm2;            // max |k|^2 per (frame, head) at [b * kn_bstride + h]
+    long long kn_bstride;
 };
 
 // pe_kernels.cu

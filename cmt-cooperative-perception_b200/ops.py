@@ -170,8 +170,10 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16)
 
 
 def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=1, strideA=0, strideB=0,
-         strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False, transpose_out=False):
-    """Raw cmt_gemm_bias_act: C = act((A B^T + bias) * alpha) with column-block output addressing."""
+         strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False, transpose_out=False,
+         norm2_max=None):
+    """Raw cmt_gemm_bias_act: C = act((A B^T + bias) * alpha) with column-block output addressing.
+    norm2_max: optional zero-initialised fp32 [batch, N/32] receiving max |row block|^2 (bf16 path)."""
     A = _cuda(A, "A")
     Bm = _cuda(Bm, "B", A.dtype)
     C = _cuda(C, "C")
@@ -183,7 +185,7 @@ def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=
     with torch.cuda.device(A.device):
         rc = lib.cmt_gemm_bias_act(_ptr(A), _ptr(Bm), _ptr(bias), _ptr(C), M, N, K, lda, ldb, ldc,
                                    cb if cb is not None else max(N, 1), cb_stride, batch, strideA, strideB, strideC,
-                                   float(alpha), flags, _dt(A.dtype), _dt(C.dtype), _stream(A))
+                                   float(alpha), flags, _dt(A.dtype), _dt(C.dtype), _ptr(norm2_max), _stream(A))
     _lib.check(rc, "cmt_gemm_bias_act")
     _count()
     return C
@@ -203,16 +205,30 @@ def linear(x, weight, bias=None, *, relu=False, alpha=1.0, out_dtype=None, force
     return out.reshape(*x.shape[:-1], N)
 
 
-def project_keys(xk, w, bias, n_layers, H, out=None):
+def project_queries(x, w, bias, H, alpha, norm2_max=None):
+    """Q = (x @ w.T + bias) * alpha, [B,Nq,H*32] in x.dtype, one GEMM batch per frame.
+    norm2_max: optional zero-initialised fp32 [B,H] receiving max_query |q|^2 per (frame, head) -- with the key
+    maxima of project_keys it bounds every attention score of the (frame, head) (static softmax shift)."""
+    B, Nq, C = x.shape
+    NO = w.shape[0]
+    assert NO == H * HEAD_DIM
+    out = torch.empty((B, Nq, NO), dtype=x.dtype, device=x.device)
+    gemm(x, w, bias, out, Nq, NO, C, lda=C, ldb=C, ldc=NO, batch=B, strideA=Nq * C, strideB=0, strideC=Nq * NO,
+         alpha=alpha, norm2_max=norm2_max)
+    return out
+
+
+def project_keys(xk, w, bias, n_layers, H, out=None, norm2_max=None):
     """K = xk @ w.T + bias for all layers at once, written in the per-head attention layout.
-    xk [B,N_kv,C]; w [n_layers*H*32, C]; -> [B, n_layers, H, N_kv, 32]."""
+    xk [B,N_kv,C]; w [n_layers*H*32, C]; -> [B, n_layers, H, N_kv, 32].
+    norm2_max: optional zero-initialised fp32 [B, n_layers*H] receiving max_token |k|^2 per (frame, layer, head)."""
     B, N_kv, C = xk.shape
     NO = w.shape[0]
     assert NO == n_layers * H * HEAD_DIM
     if out is None:
         out = torch.empty((B, n_layers, H, N_kv, HEAD_DIM), dtype=xk.dtype, device=xk.device)
     gemm(xk, w, bias, out, N_kv, NO, C, lda=C, ldb=C, ldc=HEAD_DIM, cb=HEAD_DIM, cb_stride=N_kv * HEAD_DIM,
-         batch=B, strideA=N_kv * C, strideB=0, strideC=n_layers * H * N_kv * HEAD_DIM)
+         batch=B, strideA=N_kv * C, strideB=0, strideC=n_layers * H * N_kv * HEAD_DIM, norm2_max=norm2_max)
     return out
 
 
@@ -249,11 +265,12 @@ def _workspace(dev, nbytes):
 
 
 def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False,
-               key_keep=None, tag="cross_attn"):
+               key_keep=None, q_norm2=None, k_norm2=None, tag="cross_attn"):
     """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
     vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq]).
     key_keep: optional [B,N_kv] bool/uint8, True = attend (the key_padding_mask of attention.py:76-90, whose
-    unpad_input keeps the True entries)."""
+    unpad_input keeps the True entries).
+    q_norm2 [B,H] / k_norm2 [B,L,H] fp32 (from the projections' norm2_max): enables the static softmax shift."""
     q = _cuda(q, "q")
     k = _cuda(k, "k", q.dtype)
     vt = _cuda(vt, "vt", q.dtype)
@@ -282,6 +299,14 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         key_keep = _cuda(key_keep, "key_keep")
         assert key_keep.shape == (B, N_kv), f"key_keep must be [B, N_kv] = {(B, N_kv)}, got {tuple(key_keep.shape)}"
         key_keep = key_keep.to(torch.uint8).contiguous()
+    qn = kn = None
+    kn_stride = 0
+    if q_norm2 is not None and k_norm2 is not None and dt == CMT_BF16:
+        qn = _cuda(q_norm2, "q_norm2", torch.float32)
+        k_norm2 = _cuda(k_norm2, "k_norm2", torch.float32)
+        assert qn.shape == (B, H) and k_norm2.shape == (B, L, H)
+        kn = ctypes.c_void_p(k_norm2.data_ptr() + layer * H * 4)
+        kn_stride = L * H
     ev = _profile.get(tag)
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -289,7 +314,8 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
     with torch.cuda.device(q.device):
         rc = lib.cmt_cross_attn_fwd(_ptr(q), kp, vp, _ptr(o), _ptr(lse), B, H, Nq, N_kv, kv_begin, kv_end, HD,
                                     L * H * N_kv * HEAD_DIM, N_kv * HEAD_DIM, L * H * HEAD_DIM * ld, HEAD_DIM * ld,
-                                    ld, _ptr(key_keep), dt, _dt(o_dtype), _ptr(ws), ws_bytes, _stream(q))
+                                    ld, _ptr(key_keep), _ptr(qn), kn, kn_stride, dt, _dt(o_dtype), _ptr(ws), ws_bytes,
+                                    _stream(q))
     if ev is not None:
         e1.record()
         ev.append((e0, e1))

@@ -28,11 +28,14 @@ class KVCache:
     (models/utils/cmt_transformer.py:116-125 hands the same memory/pos_embed to every layer); only
     W_k / W_v differ, so the twelve per-layer projections of the reference are two wide GEMMs here.
     k:  [B, L, H, N_kv, 32]      vt: [B, L, H, 32, ld]
+    k_norm2: [B, L, H] fp32 max_token |k|^2 (written by the K projection's epilogue), or None: with the matching
+    query maxima it lets the attention kernel use a static softmax shift (ops.cross_attn).
     """
 
-    def __init__(self, k, vt, n_kv, group=None):
+    def __init__(self, k, vt, n_kv, group=None, k_norm2=None):
         self.k = k
         self.vt = vt
+        self.k_norm2 = k_norm2
         self.n_kv = n_kv      # tokens held by THIS rank (all of them unless KV-split)
         self.group = group    # torch.distributed group when the token axis is split across ranks
 

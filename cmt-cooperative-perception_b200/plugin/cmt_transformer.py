@@ -97,9 +97,10 @@ class _CmtTransformerBase(nn.Module):
             xk_l, xv_l = xk[:, lo:hi].contiguous(), xv[:, lo:hi].contiguous()
             return KVCache(ops.project_keys(xk_l, wk, bk, L, H), ops.project_values_t(xv_l, wv, bv, L, H),
                            hi - lo, group), xv
-        k = ops.project_keys(xk, wk, bk, L, H)
+        kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
+        k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)
         vt = ops.project_values_t(xv, wv, bv, L, H)
-        return KVCache(k, vt, xk.shape[1]), xv
+        return KVCache(k, vt, xk.shape[1], k_norm2=kn2), xv
 
     def enable_kv_split(self, group=None):
         """Split the K/V token axis across the ranks of `group` (default: the WORLD group); every rank

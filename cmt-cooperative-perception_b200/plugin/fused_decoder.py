@@ -101,6 +101,11 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
     x_lp = torch.zeros((B, Nq, C), dtype=dt, device=dev)           # cast(x)
     xq_lp = query_pos.to(dt)                                       # cast(x + query_pos)
 
+    # max |q|^2 per (layer, frame, head) of the cross-attention queries: with cache.k_norm2 the attention kernel gets a
+    # bound on every score and drops the running row maximum (ops.cross_attn)
+    static_shift = cache.group is None and cache.k_norm2 is not None and dt == torch.bfloat16
+    qn2 = torch.zeros((L, B, H), dtype=torch.float32, device=dev) if static_shift else None
+
     for li, layer in enumerate(decoder.layers):
         # ---- self-attention over the queries: q = k = x + query_pos, v = x (key_pos = query_pos) ----
         sw = _mha_weights(layer.attentions[0].attn, dt)
@@ -114,10 +119,14 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
         # ---- cross-attention over the hoisted K/V cache ----
         mha = layer.attentions[1].attn
         cw = mha.compute_weights()
-        qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
-        if cache.group is None:
+        if static_shift:
+            qc = ops.project_queries(x1q_lp, cw["wq"], cw["bq"], H, _Q_SCALE, norm2_max=qn2[li])
+            ctx = ops.cross_attn(qc, cache.k, cache.vt, li, q_norm2=qn2[li], k_norm2=cache.k_norm2)
+        elif cache.group is None:
+            qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
             ctx = ops.cross_attn(qc, cache.k, cache.vt, li)
         else:
+            qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
             ctx = mha._merge_kv_split(qc, cache, li)
         ca = ops.linear(ctx, cw["wo"], cw["bo"], out_dtype=torch.float32)
         g, b, eps = _ln(layer.norms[1])

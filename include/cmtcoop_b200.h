@@ -97,13 +97,16 @@ int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_p
  *     C + z*strideC + (n / cb)*cb_stride + (n % cb)*ldc + m
  * which with cb = 32, ldc = ld gives the token-contiguous V^T layout [.., H, 32, ld] (bf16 operands and
  * output, cb % 32 == 0, N % 32 == 0, N <= 1984).
+ * norm2_max (bf16 path, or NULL): [batch][N/32] fp32, zero-initialised by the caller; the epilogue raises
+ * entry (z, n/32) to the largest squared norm of a row's 32-column block (one attention head of one
+ * query/key).  cmt_cross_attn_fwd turns the two maxima into a bound on every score (see there).
  * in_dtype bf16 -> TMA + tcgen05 kernel (fp32 accumulate in TMEM); in_dtype fp32 -> fp32
  * CUDA-core kernel (verification mode).  Requirements for bf16: K % 8 == 0, lda/ldb % 8 == 0,
  * 16-byte aligned bases, and (cb >= N or cb % 32 == 0). */
 int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N,
                       int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t cb, int64_t cb_stride,
                       int batch, int64_t strideA, int64_t strideB, int64_t strideC, float alpha,
-                      int flags, int in_dtype, int out_dtype, void* stream);
+                      int flags, int in_dtype, int out_dtype, float* norm2_max, void* stream);
 
 /* ---- K3: flash cross-attention ------------------------------------------------------
  * Replaces flash_attn_unpadded_kvpacked_func as called by FlashAttention.forward
@@ -116,6 +119,12 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
  * key_keep: [B,N_kv] bytes, 1 = attend, 0 = padded key, or NULL.  This is the key_padding_mask branch of
  *      FlashAttention.forward (attention.py:76-90: unpad_input + cu_seqlens_k); dropping a key from the packed
  *      sequence and giving it weight zero are the same softmax.  A query with no attended key gets o = 0.
+ * q_norm2_max [B*H], k_norm2_max (entry (b,h) at b*kn_bstride + h), both or neither NULL: upper bounds of
+ *      |q|^2 and |k|^2 per (frame, head) as written by cmt_gemm_bias_act(norm2_max).  |q.k| <= |q||k| bounds
+ *      every score of the (frame, head); when that bound is <= 60 (log2 units) the bf16 kernel uses it as a
+ *      fixed softmax shift and skips the running row maximum and the accumulator rescale (same result: the
+ *      softmax is shift-invariant, and all weights stay normal numbers); larger bounds and NULL use the
+ *      online softmax.
  * lse: [B,H,Nq] fp32 natural-log sum-exp of the scaled scores over the attended tokens, or NULL
  * dtype bf16 -> tcgen05 kernel, work split over all SMs along the KV axis with partials in
  * `workspace` (cmt_cross_attn_workspace_bytes) merged by a second kernel; dtype fp32 -> fp32
@@ -124,7 +133,8 @@ size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens);
 int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, float* lse, int B,
                        int H, int Nq, int N_kv, int kv_begin, int kv_end, int64_t q_ld,
                        int64_t k_bstride, int64_t k_hstride, int64_t v_bstride, int64_t v_hstride,
-                       int64_t v_ld, const unsigned char* key_keep, int dtype, int o_dtype,
+                       int64_t v_ld, const unsigned char* key_keep, const float* q_norm2_max,
+                       const float* k_norm2_max, int64_t kn_bstride, int dtype, int o_dtype,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Log-sum-exp merge of G partial attention results (KV-token split across GPUs or streams):

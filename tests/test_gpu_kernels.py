@@ -263,3 +263,62 @@ def test_cross_attention_key_padding_mask(mode):
                         torch.nn.functional.pad(vt[2:3, ..., idx], (0, (-len(idx)) % 8)).contiguous().to(DEV), 0,
                         o_dtype=torch.float32)
     assert _rel(o[2:3], o2.cpu()) < tol
+
+
+def test_gemm_norm2_max():
+    """norm2_max of cmt_gemm_bias_act: running max over rows of the squared norm of each 32-column block."""
+    g = torch.Generator().manual_seed(8)
+    B, M, N, K = 3, 333, 256, 256
+    x = torch.randn(B, M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / 16).bfloat16()
+    b = torch.randn(N, generator=g)
+    n2 = torch.zeros(B, N // 32, device=DEV)
+    q = ops.project_queries(x.to(DEV), w.to(DEV), b.to(DEV), N // 32, 0.5, norm2_max=n2)
+    want = ((x.float() @ w.float().T + b) * 0.5)
+    assert _rel(q.float(), want) < 4e-3
+    want_n2 = want.view(B, M, N // 32, 32).pow(2).sum(-1).amax(1)
+    assert torch.allclose(n2.cpu(), want_n2, rtol=2e-3)
+    # per-head K layout
+    kn2 = torch.zeros(B, 1, N // 32, device=DEV)
+    k = ops.project_keys(x.to(DEV), w.to(DEV), b.to(DEV), 1, N // 32, norm2_max=kn2)
+    want_k = (x.float() @ w.float().T + b).view(B, M, N // 32, 32)
+    assert torch.allclose(kn2.cpu()[:, 0], want_k.pow(2).sum(-1).amax(1), rtol=2e-3)
+    assert _rel(k[:, 0].float().permute(0, 2, 1, 3), want_k) < 4e-3
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_cross_attention_static_shift(masked):
+    """Static softmax shift: with the operand-norm maxima the kernel uses the Cauchy-Schwarz score bound as a fixed
+    shift where it is <= 60 and the online softmax elsewhere.  Frame 0: small scores (static path); frame 1: large
+    scores (bound > 60: online path); frame 2: mid-size norms.  Same result as the reference either way, and as the
+    call without norms."""
+    B, H, Nq, N_kv = 3, 8, 300, 3000
+    g = torch.Generator().manual_seed(23)
+    q = torch.randn(B, Nq, H * 32, generator=g) * 0.6
+    k = torch.randn(B, 1, H, N_kv, 32, generator=g)
+    q[1] *= 4.0
+    k[1] *= 3.0          # score std ~ 7 * sqrt(32) / ... -> bound far above 60
+    k[2] *= 2.0
+    q, k = q.bfloat16(), k.bfloat16()
+    vt = torch.randn(B, 1, H, 32, N_kv, generator=g).bfloat16()
+    keep = None
+    if masked:
+        keep = torch.rand(B, N_kv, generator=g) > 0.25
+        keep[0, :130] = False
+    qn2 = q.float().view(B, Nq, H, 32).pow(2).sum(-1).amax(1).contiguous()
+    kn2 = k.float().pow(2).sum(-1).amax(-1).contiguous()            # [B,1,H]
+    bound = (qn2 * kn2[:, 0]).sqrt()
+    assert bound[0].max() < 60 and bound[1].min() > 60             # both paths are exercised
+    qh = q.double().view(B, Nq, H, 32).permute(0, 2, 1, 3)
+    s = qh @ k.double()[:, 0].transpose(-1, -2) * math.log(2.0)
+    if masked:
+        s = s.masked_fill(~keep[:, None, None, :], float("-inf"))
+    want = (torch.softmax(s, -1) @ vt.double()[:, 0].transpose(-1, -2)).permute(0, 2, 1, 3).reshape(B, Nq, H * 32)
+    kw = dict(o_dtype=torch.float32, return_lse=True, key_keep=None if keep is None else keep.to(DEV))
+    o, lse = ops.cross_attn(q.to(DEV), k.to(DEV), vt.to(DEV), 0, q_norm2=qn2.to(DEV), k_norm2=kn2.to(DEV), **kw)
+    o0, lse0 = ops.cross_attn(q.to(DEV), k.to(DEV), vt.to(DEV), 0, **kw)
+    torch.cuda.synchronize()
+    assert _rel(o, want) < 6e-3, _rel(o, want)
+    assert _rel(o, o0) < 6e-3
+    assert (lse.cpu() - torch.logsumexp(s, -1)).abs().max() < 6e-3
+    assert (lse - lse0).abs().max() < 6e-3

@@ -46,6 +46,11 @@ if which == "attnonly":   # attention alone on random K / V^T (A/B runs of kerne
     q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
     timed("attn", lambda: ops.cross_attn(q, k, vt, 0))
     timed("attn", lambda: ops.cross_attn(q, k, vt, 0))
+    # static softmax shift: score bound from the operand norms (what the projection epilogues provide)
+    qn2 = q.float().view(B, Nq, H, 32).pow(2).sum(-1).amax(1).contiguous()
+    kn2 = k.float().pow(2).sum(-1).amax(-1).contiguous()
+    print("score bound (log2 units): max %.1f" % float((qn2 * kn2[:, 0]).sqrt().max()), flush=True)
+    timed("attn_static", lambda: ops.cross_attn(q, k, vt, 0, q_norm2=qn2, k_norm2=kn2))
     # per-CTA cycle counts of one launch -> SM clock under this kernel (power-limited, well below the 1965 MHz maximum)
     import ctypes
     from cmtcoop_b200 import _lib
