@@ -46,5 +46,5 @@ def test_entries_refuse_without_sm100():
     assert lib.cmt_check_device(0) == -3
     rc = lib.cmt_coop_max(None, None, None, 0, None)
     assert rc == -3 and "no CUDA device" in _lib.last_error() or "sm_100" in _lib.last_error()
-    rc = lib.cmt_gemm_bias_act(None, None, None, None, 1, 1, 8, 8, 8, 1, 1, 0, 1, 0, 0, 0, 1.0, 0, 1, 1, None)
+    rc = lib.cmt_gemm_bias_act(None, None, None, None, 1, 1, 8, 8, 8, 1, 1, 0, 1, 0, 0, 0, 1.0, 0, 1, 1, None, None)
     assert rc == -3
