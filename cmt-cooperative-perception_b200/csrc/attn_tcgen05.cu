@@ -39,10 +39,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
 
 // The same cubic on a PAIR of inputs with the packed fp32 instructions (FADD2 / FFMA2): 2 clamps, 3 FADD2,
 // 3 FFMA2 and 2 integer ops for two exponentials, i.e. ~5 issue slots per exponential and no MUFU slot.
+// kClamp = false: the caller guarantees x >= -126 (static-shift path: scores in [-60, 60], masked tail set to -126).
+template <bool kClamp = true>
 __device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& e0, float& e1) {
-    float x0, x1;
-    unpack_f32x2(x2, x0, x1);
-    x2 = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    if (kClamp) {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        x2 = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    }
     const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
     const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
     const uint64_t m1 = pack_f32x2(-1.0f, -1.0f);
@@ -83,6 +87,7 @@ struct TcAttnParams {
     const float* q_norm2;
     const float* k_norm2;
     long long kn_bstride;
+    int* unsafe_flags; // [gridDim.x] written by the static kernel (1 = this CTA's range holds items left to the online kernel)
     long long* trace; // debug: clock64 event trace of CTA 0 (three-warpgroup kernel), nullptr = off
 };
 constexpr int TRACE_STEPS = 96;
@@ -215,11 +220,17 @@ constexpr float STATIC_LIMIT = 60.0f;
 
 // kMask: key padding mask variant (the unmasked instantiation carries none of its code: even an untaken mask
 // branch in the softmax loop cost 12 % on the 128-register budget).
-template <bool kMask>
+// kStatic: static-shift variant.  When the caller supplies the operand norm maxima, BOTH instantiations are launched
+// back to back over the same ranges: <kStatic = true> processes the items whose score bound is at most
+// STATIC_LIMIT and records per CTA whether it skipped any item; <false> processes exactly those (its CTAs return at
+// once when their flag is clear).  Keeping the two softmax loops in separate kernels matters for the same reason as
+// kMask: sharing a kernel cost the online loop 8 %.
+template <bool kMask, bool kStatic>
 __global__ void __launch_bounds__(attndb::THREADS, 1)
 tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
     using namespace attndb;
+    if (!kStatic && p.q_norm2 != nullptr && p.unsafe_flags[blockIdx.x] == 0) return;   // the static kernel took everything
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -271,15 +282,26 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const long long G = gridDim.x;
     const long long pos_begin = range_start(p, blockIdx.x, G);
     const long long pos_end = range_start(p, blockIdx.x + 1, G);
+    // Which items are this instantiation's?  Without norms: everything goes to the online kernel.  With norms: the item's
+    // Cauchy-Schwarz score bound |q||k| (norms of the fp32 projection outputs; + 2^-7 covers the two bf16 roundings the
+    // MMA operands went through) decides.  Every role evaluates the same predicate, so skipped segments touch no barrier.
+    auto mine = [&](int item) -> bool {
+        if (p.q_norm2 == nullptr) return !kStatic;
+        const int hb = item / p.qblocks;   // b * H + h
+        const float bound = sqrtf(__ldg(p.q_norm2 + hb) * __ldg(p.k_norm2 + static_cast<long long>(hb / p.H) * p.kn_bstride + hb % p.H)) * 1.0079f + 1e-3f;
+        return (bound <= STATIC_LIMIT) == kStatic;
+    };
 
     if (warp == W_TMA) {
         // ----------------------------- TMA producer -----------------------------
         const bool leader = elect_one();
         uint32_t kc = 0, vc = 0, seg = 0;
+        int skipped = 0;
         for (long long pos = pos_begin; pos < pos_end;) {
             const int item = static_cast<int>(pos / p.T);
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            if (!mine(item)) { pos += n; skipped = 1; continue; }
             const int qb = item % p.qblocks;
             const int h = (item / p.qblocks) % p.H;
             const int b = item / (p.qblocks * p.H);
@@ -316,6 +338,8 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             pos += n;
             ++seg;
         }
+        // tell the online kernel whether this CTA's range holds items the static kernel left to it
+        if (kStatic && leader && p.unsafe_flags != nullptr) p.unsafe_flags[blockIdx.x] = skipped;
     } else if (warp >= W_MMA && warp < W_MMA + NISS) {
         // ------------- MMA issuers: warp W_MMA + ii serves the warpgroups i with i % NISS == ii -------------
         const int ii = warp - W_MMA;
@@ -331,6 +355,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int item = static_cast<int>(pos / p.T);
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
+            if (!mine(item)) { pos += n; continue; }
             const int qb = item % p.qblocks;
             int nact = (p.Nq - qb * QBLK + 127) >> 7;   // warpgroups with queries; the others only release stages
             nact = nact > NWG ? NWG : nact;
@@ -428,6 +453,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
             const int qb = item % p.qblocks;
             pos += n;
+            if (!mine(item)) continue;
             if (qb * QBLK + wg * 128 >= p.Nq) continue;     // this warpgroup's tile is past the last query
             if (qb * QBLK + wg * 128 + (warp & 3) * 32 >= p.Nq) {
                 // all 32 rows of this warp are past the last query (900 queries: three warps of the eighth tile):
@@ -445,10 +471,8 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const unsigned long long* mask_row = kMask ? p.mask_bits + static_cast<long long>(hb / p.H) * p.T : nullptr;
             float m = -INFINITY, l = 0.0f;
 
-            // One KV step of this thread's row.  kStatic: the softmax shift m is the item's Cauchy-Schwarz score bound
-            // (no row maximum, no rescale of O); otherwise the online form with lazy rescale.
-            auto step = [&](auto static_tag, int jj) {
-                constexpr bool kStatic = decltype(static_tag)::value;
+            // One KV step of this thread's row.
+            auto step = [&](int jj) {
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
                 CMT_S_WAIT(&my_s_full[bsel], (g >> 1) & 1);
@@ -470,11 +494,14 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                         if (!((mhi >> i) & 1u)) s[1][i] = 0xff800000u;
                     }
                 } else if (valid < KT) {
+                    // keys past kv_end: -inf, or -126 on the static path (2^-126 against weights >= 2^-60 is nothing,
+                    // and the polynomial exponentials there run without their underflow clamp)
+                    const uint32_t gone = kStatic ? 0xc2fc0000u : 0xff800000u;
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+                            if (c * 32 + i >= valid) s[c][i] = gone;
                 }
                 if (!kStatic) {
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -521,10 +548,11 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const uint64_t x2 = add_f32x2(pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), neg_m2);
+                        uint64_t x2 = pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
+                        if (!kStatic) x2 = add_f32x2(x2, neg_m2);   // static: |s| <= 60, 2^s needs no shift at all
                         float e0, e1;
                         if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-                            ex2_poly_pair(x2, e0, e1);
+                            ex2_poly_pair<(!kStatic || kMask)>(x2, e0, e1);
                         } else {
                             float x0, x1;
                             unpack_f32x2(x2, x0, x1);
@@ -548,20 +576,11 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 ++g;
             };
 
-            // static bound of every score of the item: |q . k| <= |q| |k| over the bf16-rounded operands the MMAs see
-            // (the norms come from the fp32 projection outputs: + 2^-7 covers the two roundings).  Scores then lie in
-            // [-m, m], so with m <= STATIC_LIMIT every weight 2^(s - m) stays a normal number.
-            bool stat = false;
-            if (p.q_norm2 != nullptr) {
-                const float bound = sqrtf(__ldg(p.q_norm2 + hb) * __ldg(p.k_norm2 + static_cast<long long>(hb / p.H) * p.kn_bstride + hb % p.H)) * 1.0079f + 1e-3f;
-                stat = bound <= STATIC_LIMIT;
-                if (stat) m = bound;
-            }
-            if (stat) {
-                for (int jj = 0; jj < n; ++jj) step(std::true_type{}, jj);
-            } else {
-                for (int jj = 0; jj < n; ++jj) step(std::false_type{}, jj);
-            }
+            // static variant: every score of the item lies in [-STATIC_LIMIT, STATIC_LIMIT] (see `mine`), so the weights
+            // 2^s are normal numbers as they are: the softmax is shift-invariant, hence no row maximum, no subtraction
+            // and no rescale of O; the partial's LSE is just log2 of the sum (m = 0).
+            if (kStatic) m = 0.0f;
+            for (int jj = 0; jj < n; ++jj) step(jj);
             // segment epilogue: normalised partial + log2-sum-exp into the workspace
             mbar_wait(&o_full[wg], seg & 1);
             ++seg;
@@ -689,8 +708,8 @@ size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     long long G;
     attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid, &G);
     const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
-    // partials + alignment + the packed key mask (used only when a key_padding_mask is given)
-    return slots * p.qblk * 33 * sizeof(float) + 256 + static_cast<size_t>(B) * p.T * 8 + 8;
+    // partials + alignment + the packed key mask (used only when a key_padding_mask is given) + per-CTA flags
+    return slots * p.qblk * 33 * sizeof(float) + 256 + static_cast<size_t>(B) * p.T * 8 + 8 + static_cast<size_t>(grid) * 4 + 16;
 }
 
 int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -725,23 +744,27 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     p.k_norm2 = a.k_norm2;
     p.kn_bstride = a.kn_bstride;
     p.mask_bits = nullptr;
+    uintptr_t tail = (reinterpret_cast<uintptr_t>(p.part_lse + slots * p.qblk) + 7) & ~uintptr_t(7);
     if (a.key_keep != nullptr) {
-        uintptr_t mb = (reinterpret_cast<uintptr_t>(p.part_lse + slots * p.qblk) + 7) & ~uintptr_t(7);
-        unsigned long long* bits = reinterpret_cast<unsigned long long*>(mb);
+        unsigned long long* bits = reinterpret_cast<unsigned long long*>(tail);
         const long long n = static_cast<long long>(a.B) * p.T;
         pack_key_mask_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(a.key_keep, bits, a.B, a.N_kv, a.kv_begin,
                                                                                 a.kv_end, p.T);
         CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(mask)");
         p.mask_bits = bits;
     }
+    p.unsafe_flags = reinterpret_cast<int*>(tail + static_cast<size_t>(a.B) * p.T * 8 + 8);
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_attn_db_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
-        e = cudaFuncSetAttribute(tc_attn_db_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db<mask>)");
-
+        const void* fns[4] = {reinterpret_cast<const void*>(&tc_attn_db_kernel<false, false>),
+                              reinterpret_cast<const void*>(&tc_attn_db_kernel<false, true>),
+                              reinterpret_cast<const void*>(&tc_attn_db_kernel<true, false>),
+                              reinterpret_cast<const void*>(&tc_attn_db_kernel<true, true>)};
+        for (const void* f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
+        }
         attr_done = true;
     }
     CUtensorMap tq, tk, tv;
@@ -767,10 +790,19 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
         int rc = encode_tma_bf16(&tv, a.vt, 4, dims, strides, box, 128);
         if (rc) return rc;
     }
-    if (p.mask_bits != nullptr)
-        tc_attn_db_kernel<true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    const bool masked = p.mask_bits != nullptr;
+    if (p.q_norm2 != nullptr) {
+        // static-shift kernel first (items with a score bound <= STATIC_LIMIT), then the online kernel for the rest
+        if (masked)
+            tc_attn_db_kernel<true, true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        else
+            tc_attn_db_kernel<false, true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05, static shift)");
+    }
+    if (masked)
+        tc_attn_db_kernel<true, false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     else
-        tc_attn_db_kernel<false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        tc_attn_db_kernel<false, false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
     const long long total = static_cast<long long>(a.B) * a.H * p.qblocks * p.qblk * 8;
     long long mblocks = (total + 255) / 256;
