@@ -320,7 +320,8 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         e1.record()
         ev.append((e0, e1))
     _lib.check(rc, "cmt_cross_attn_fwd")
-    _count((2 if dt == CMT_BF16 else 1) + (1 if key_keep is not None and dt == CMT_BF16 else 0))
+    # tcgen05 path: [mask pack] + [static-shift kernel] + online kernel + merge
+    _count((2 if dt == CMT_BF16 else 1) + (1 if key_keep is not None and dt == CMT_BF16 else 0) + (1 if qn is not None else 0))
     return (o, lse) if return_lse else o
 
 
