@@ -666,7 +666,11 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
 // (An "independent warpgroup" variant -- one K/V stream per warpgroup, items of 128 queries, 3 ranges per CTA -- was
 // built and measured in round 1: parity-green but 1108 vs 973 us.  A 4-query tail tile still loads one SM
 // sub-partition with three active warps, so it costs a full tile; see DESIGN.md.)
-static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p, int* grid, long long* slots_out) {
+// static_shift: the call carries operand norms (the static-shift kernel runs the ranges): its full step is cheaper, so
+// the chain-bound last query block weighs relatively more... measured optimum 10:7 against 4:3 for the online kernel
+// (us per launch, B=8: static 842 @10:7 vs 858 @4:3; online 951 @4:3 vs 961 @10:7).
+static void attn_plan(int B, int H, int Nq, int n_tok, int sms, bool static_shift, TcAttnParams* p, int* grid,
+                      long long* slots_out) {
     const int per_cta = 1;
     p->qblk = attndb::QBLK;
     p->kt = attndb::KT;
@@ -677,8 +681,8 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, TcAttnParams* p,
     const int rows_last = Nq - (p->qblocks - 1) * p->qblk;
     // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
     // own chain, ~3/4 of that
-    p->w_full = 4;
-    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? 3 : 4;
+    p->w_full = static_shift ? 10 : 4;
+    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? (static_shift ? 7 : 3) : p->w_full;
     p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
     p->Wtot = static_cast<long long>(B) * H * p->Wg;
     // no more slots than full-weight steps, so that a range is never shorter than the widest step
@@ -703,10 +707,12 @@ int tc_attn_set_timing_buffer(long long* dev_buf) { g_trace_buf = dev_buf; retur
 
 size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
-    TcAttnParams p{};
+    TcAttnParams p{}, p2{};
     int grid;
     long long G;
-    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), &p, &grid, &G);
+    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), false, &p, &grid, &G);
+    attn_plan(B, H, Nq, n_kv_tokens, device_sm_count(), true, &p2, &grid, &G);
+    if (p2.S_max > p.S_max) p.S_max = p2.S_max;   // either plan fits
     const size_t slots = static_cast<size_t>(B) * H * p.qblocks * p.S_max;
     // partials + alignment + the packed key mask (used only when a key_padding_mask is given) + per-CTA flags
     return slots * p.qblk * 33 * sizeof(float) + 256 + static_cast<size_t>(B) * p.T * 8 + 8 + static_cast<size_t>(grid) * 4 + 16;
@@ -724,7 +730,7 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     TcAttnParams p{};
     int grid;
     long long G;
-    attn_plan(a.B, a.H, a.Nq, n_tok, device_sm_count(), &p, &grid, &G);
+    attn_plan(a.B, a.H, a.Nq, n_tok, device_sm_count(), a.q_norm2 != nullptr && a.k_norm2 != nullptr, &p, &grid, &G);
     p.B = a.B;
     p.H = a.H;
     p.Nq = a.Nq;
