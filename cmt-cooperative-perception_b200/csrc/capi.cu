@@ -269,6 +269,13 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
 }
 
 // debug hook (not part of the public header): per-phase clock64 accounting of tc_attn_kernel, CTA 0
+int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
+                       int L, int M, int NH, int HC, int CMAX, float eps, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    CMT_CHECK_ARG(h && gamma && beta && w2 && b2 && out, "cmt_task_head_tail: null pointer");
+    return launch_task_head_tail(h, gamma, beta, w2, b2, out, L, M, NH, HC, CMAX, eps, static_cast<cudaStream_t>(stream));
+}
+
 int cmt_debug_attn_timing(void* dev_buf_32xi64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_32xi64)); }
 
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B, int H,

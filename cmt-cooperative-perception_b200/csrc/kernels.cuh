@@ -54,6 +54,8 @@ int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, floa
 int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
                          void* yadd, int lp_dtype, cudaStream_t stream);
+int launch_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
+                          int L, int M, int NH, int HC, int CMAX, float eps, cudaStream_t stream);
 // simt_kernels.cu
 int launch_simt_gemm(const GemmArgs& g, int batch, int in_dtype, cudaStream_t stream);
 int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);

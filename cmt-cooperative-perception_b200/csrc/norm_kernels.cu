@@ -128,4 +128,80 @@ int launch_add_layernorm(const float* x, const float* r, const float* gamma, con
     return CMT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Task-head tail (SeparateTaskHead, cmt_head.py:116-150 + GroupLayerNorm1d :53-94, final_kernel = 1): after the first
+// grouped 1x1 conv (a per-decoder-layer GEMM, h = x W1^T), every (layer, query row, output head) needs
+//   y = ReLU(LN_64(h) * gamma + beta),   out[o] = y . w2[o] + b2[o]        (o < c_out <= CMAX)
+// Eager torch runs this as ~10 elementwise / reduction passes over the 66 MB h tensor plus an einsum (0.45 ms per
+// forward at B = 8); here one warp owns a (layer, row): per head a coalesced 256-byte read, two shuffle reductions for
+// the statistics, the affine + ReLU in registers and CMAX 64-long dot products against w2 held in shared memory.
+// fp32 throughout (these outputs feed the top-k).
+constexpr int TH_HC = 64;   // hidden channels per head (head_conv = 64 in every reference config)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) task_head_tail_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, float* __restrict__ out, int M,
+                                                             int NH, int CMAX, float eps) {
+    extern __shared__ float th_smem[];
+    const int l = blockIdx.y;
+    float* w2s = th_smem;                       // [NH][CMAX][64]
+    float* gs = w2s + NH * CMAX * TH_HC;        // [NH][64]
+    float* bs = gs + NH * TH_HC;                // [NH][64]
+    float* b2s = bs + NH * TH_HC;               // [NH][CMAX]
+    for (int i = threadIdx.x; i < NH * CMAX * TH_HC; i += blockDim.x) w2s[i] = w2[static_cast<long long>(l) * NH * CMAX * TH_HC + i];
+    for (int i = threadIdx.x; i < NH * TH_HC; i += blockDim.x) {
+        gs[i] = gamma[l * NH * TH_HC + i];
+        bs[i] = beta[l * NH * TH_HC + i];
+    }
+    for (int i = threadIdx.x; i < NH * CMAX; i += blockDim.x) b2s[i] = b2[l * NH * CMAX + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int m = blockIdx.x * nwarp + warp; m < M; m += gridDim.x * nwarp) {
+        const float* hrow = h + (static_cast<long long>(l) * M + m) * NH * TH_HC;
+        float* orow = out + (static_cast<long long>(l) * M + m) * NH * CMAX;
+        for (int hd = 0; hd < NH; ++hd) {
+            const float2 v = *reinterpret_cast<const float2*>(hrow + hd * TH_HC + 2 * lane);
+            const float mu = warp_sum(v.x + v.y) * (1.0f / TH_HC);
+            const float d0 = v.x - mu, d1 = v.y - mu;
+            const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / TH_HC);
+            const float sd = sqrtf(var + eps);
+            const float2 g = *reinterpret_cast<const float2*>(gs + hd * TH_HC + 2 * lane);
+            const float2 b = *reinterpret_cast<const float2*>(bs + hd * TH_HC + 2 * lane);
+            const float y0 = fmaxf(d0 / sd * g.x + b.x, 0.0f), y1 = fmaxf(d1 / sd * g.y + b.y, 0.0f);
+            float mine = 0.0f;   // lane o keeps output o
+            for (int o = 0; o < CMAX; ++o) {
+                const float2 w = *reinterpret_cast<const float2*>(w2s + (hd * CMAX + o) * TH_HC + 2 * lane);
+                const float acc = warp_sum(y0 * w.x + y1 * w.y);
+                if (lane == o) mine = acc;
+            }
+            if (lane < CMAX) orow[hd * CMAX + lane] = mine + b2s[hd * CMAX + lane];
+        }
+    }
+}
+
+int launch_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
+                          int L, int M, int NH, int HC, int CMAX, float eps, cudaStream_t stream) {
+    CMT_CHECK_ARG(HC == TH_HC, "cmt_task_head_tail: head_conv must be %d (got %d)", TH_HC, HC);
+    CMT_CHECK_ARG(L > 0 && M > 0 && NH > 0 && CMAX > 0 && CMAX <= 32, "cmt_task_head_tail: bad shape L=%d M=%d NH=%d CMAX=%d", L, M,
+                  NH, CMAX);
+    const size_t smem = static_cast<size_t>(NH) * (CMAX * TH_HC + 2 * TH_HC + CMAX) * sizeof(float);
+    CMT_CHECK_ARG(smem <= 200 * 1024, "cmt_task_head_tail: weights do not fit in shared memory");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(task_head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(task_head_tail)");
+    }
+    int bx = (M + 7) / 8;
+    const int cap = device_sm_count() * 4 / (L > 0 ? L : 1) + 1;
+    if (bx > cap) bx = cap;
+    task_head_tail_kernel<<<dim3(bx, L), 256, smem, stream>>>(h, gamma, beta, w2, b2, out, M, NH, CMAX, eps);
+    CMT_LAUNCH_CHECK("cmt_task_head_tail");
+    return CMT_OK;
+}
+
 }  // namespace cmt

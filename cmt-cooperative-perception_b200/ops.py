@@ -376,3 +376,21 @@ def add_layernorm(x, r, gamma, beta, eps=1e-5, *, gamma2=None, beta2=None, y2=No
     _lib.check(rc, "cmt_add_layernorm")
     _count()
     return y, y2, ylp, yadd
+
+
+def task_head_tail(h, gamma, beta, w2, b2, eps):
+    """ReLU(GroupLN(h) * gamma + beta) . w2 + b2 for every (layer, row, output head) in one launch (cmt_head.py:116-150,
+    :53-94).  h [L,M,NH,64] fp32; gamma/beta [L,NH,64]; w2 [L,NH,CMAX,64]; b2 [L,NH,CMAX] -> [L,M,NH,CMAX] fp32."""
+    h = _cuda(h, "h", torch.float32)
+    L, M, NH, HC = h.shape
+    CMAX = w2.shape[2]
+    args = [_cuda(t, n, torch.float32) for t, n in ((gamma, "gamma"), (beta, "beta"), (w2, "w2"), (b2, "b2"))]
+    assert args[0].shape == (L, NH, HC) and args[1].shape == (L, NH, HC)
+    assert args[2].shape == (L, NH, CMAX, HC) and args[3].shape == (L, NH, CMAX)
+    out = torch.empty((L, M, NH, CMAX), dtype=torch.float32, device=h.device)
+    lib = _lib.load()
+    with torch.cuda.device(h.device):
+        rc = lib.cmt_task_head_tail(_ptr(h), *[_ptr(a) for a in args], _ptr(out), L, M, NH, HC, CMAX, float(eps), _stream(h))
+    _lib.check(rc, "cmt_task_head_tail")
+    _count()
+    return out

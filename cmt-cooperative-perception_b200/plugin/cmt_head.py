@@ -128,6 +128,12 @@ class SeparateTaskHead(nn.Module):
         L, B, Q, C = x.shape
         names, couts, hc, w1t, g, b, w2, b2, eps = self._k1_weights()
         h = torch.bmm(x.reshape(L, B * Q, C), w1t).view(L, B * Q, len(names), hc)
+        if x.is_cuda and hc == 64 and w2.shape[2] <= 32:
+            # group-LN + ReLU + second conv of all six outputs in one launch (fp32, libcmtcoop_b200)
+            out = ops.task_head_tail(h.contiguous(), g.reshape(L, len(names), hc).contiguous(),
+                                     b.reshape(L, len(names), hc).contiguous(), w2.contiguous(),
+                                     b2.reshape(L, len(names), -1).contiguous(), eps)
+            return {n: out[:, :, i, :co].reshape(L, B, Q, co) for i, (n, co) in enumerate(zip(names, couts))}
         mu = h.mean(-1, keepdim=True)
         var = (h - mu).pow(2).mean(-1, keepdim=True)
         y = torch.relu((h - mu) / (var + eps).sqrt() * g + b)

@@ -154,6 +154,18 @@ int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const 
                       int M, int C, float* y, const float* gamma2, const float* beta2, float* y2,
                       const float* add, void* ylp, void* yadd, int lp_dtype, void* stream);
 
+/* ---- task heads: group-LN + ReLU + second 1x1 conv --------------------------------------
+ * The tail of SeparateTaskHead (models/dense_heads/cmt_head.py:116-150 with GroupLayerNorm1d :53-94,
+ * final_kernel = 1) after the first grouped 1x1 conv, for all output heads at once:
+ *   h:     [L, M, NH, HC] fp32   first-conv output, L = decoder layers (conv groups), M = B*Nq rows,
+ *                                NH = output heads (center, height, dim, rot, vel, cls_logits), HC = 64
+ *   gamma, beta: [L, NH, HC]     GroupLayerNorm1d affine;  eps: its epsilon (1e-6)
+ *   w2:    [L, NH, CMAX, HC], b2: [L, NH, CMAX]   second conv, zero-padded to CMAX <= 32 outputs per head
+ *   out:   [L, M, NH, CMAX] fp32 = ReLU(LN(h) * gamma + beta) . w2 + b2 */
+int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2,
+                       const float* b2, float* out, int L, int M, int NH, int HC, int CMAX, float eps,
+                       void* stream);
+
 /* ---- cooperative V2I merge ----------------------------------------------------------
  * out = max(nan_to_num(a), nan_to_num(b)) element-wise (cmt_head_coop.py:358,383-389). */
 int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream);

@@ -322,3 +322,22 @@ def test_cross_attention_static_shift(masked):
     assert _rel(o, o0) < 6e-3
     assert (lse.cpu() - torch.logsumexp(s, -1)).abs().max() < 6e-3
     assert (lse - lse0).abs().max() < 6e-3
+
+
+def test_task_head_tail():
+    """cmt_task_head_tail against the eager GroupLayerNorm1d / ReLU / 1x1 conv arithmetic (cmt_head.py:53-94, 116-150)."""
+    g = torch.Generator().manual_seed(4)
+    L, M, NH, HC, CMAX = 6, 1801, 6, 64, 10
+    h = torch.randn(L, M, NH, HC, generator=g) * 3 + 0.5
+    gamma, beta = torch.randn(L, NH, HC, generator=g), torch.randn(L, NH, HC, generator=g)
+    w2, b2 = torch.randn(L, NH, CMAX, HC, generator=g) * 0.2, torch.randn(L, NH, CMAX, generator=g)
+    eps = 1e-6
+    hd = h.double()
+    mu = hd.mean(-1, keepdim=True)
+    var = (hd - mu).pow(2).mean(-1, keepdim=True)
+    y = torch.relu((hd - mu) / (var + eps).sqrt() * gamma.double()[:, None] + beta.double()[:, None])
+    want = torch.einsum("lmhc,lhoc->lmho", y, w2.double()) + b2.double()[:, None]
+    d = lambda t: t.to(DEV)
+    out = ops.task_head_tail(d(h), d(gamma), d(beta), d(w2), d(b2), eps)
+    assert out.shape == (L, M, NH, CMAX)
+    assert torch.allclose(out.cpu().double(), want, atol=2e-5, rtol=1e-5)
