@@ -174,11 +174,25 @@ __global__ void __launch_bounds__(256) task_head_tail_kernel(const float* __rest
             const float2 g = *reinterpret_cast<const float2*>(gs + hd * TH_HC + 2 * lane);
             const float2 b = *reinterpret_cast<const float2*>(bs + hd * TH_HC + 2 * lane);
             const float y0 = fmaxf(d0 / sd * g.x + b.x, 0.0f), y1 = fmaxf(d1 / sd * g.y + b.y, 0.0f);
+            // the CMAX dot products: partial sums of four outputs at a time go through the butterfly together (the
+            // shuffles of one reduction are a dependent chain; four interleaved chains keep the warp issuing)
             float mine = 0.0f;   // lane o keeps output o
-            for (int o = 0; o < CMAX; ++o) {
-                const float2 w = *reinterpret_cast<const float2*>(w2s + (hd * CMAX + o) * TH_HC + 2 * lane);
-                const float acc = warp_sum(y0 * w.x + y1 * w.y);
-                if (lane == o) mine = acc;
+            for (int o0 = 0; o0 < CMAX; o0 += 4) {
+                float acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o = min(o0 + j, CMAX - 1);
+                    const float2 w = *reinterpret_cast<const float2*>(w2s + (hd * CMAX + o) * TH_HC + 2 * lane);
+                    acc[j] = y0 * w.x + y1 * w.y;
+                }
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], sft);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (lane == o0 + j) mine = acc[j];
             }
             if (lane < CMAX) orow[hd * CMAX + lane] = mine + b2s[hd * CMAX + lane];
         }
