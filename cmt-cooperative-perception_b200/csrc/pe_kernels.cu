@@ -34,7 +34,9 @@ __device__ __forceinline__ float div_by_const(float a, float b, float inv) {
 // registers, depth bins and pixel abscissae come from two small shared-memory tables (filled with true
 // divisions once per block), and the normalising division is a 3-instruction correctly rounded sequence.
 // ~9 instructions per output value, so the kernel is bound by the HBM write instead of by issue.
-template <bool kBf16>
+// kBins = depth bins per thread-item: 16 (D % 16 == 0: 96 bytes of bf16 = three 256-bit stores, every store instruction
+// writes whole 32-byte sectors) or 8 (48 bytes = three 128-bit stores at a 48-byte lane stride: half-filled sectors).
+template <bool kBf16, int kBins>
 __global__ void __launch_bounds__(256) ray_pe_kernel(const float* __restrict__ img2lidar,
                                                      void* __restrict__ out, RayPeParams p) {
     extern __shared__ float sm[];
@@ -53,16 +55,17 @@ __global__ void __launch_bounds__(256) ray_pe_kernel(const float* __restrict__ i
         for (int o = 0; o < 4; ++o) M[c][o] = __ldg(img2lidar + cam * 16 + c * 4 + o);
     __syncthreads();
     const float v = (static_cast<float>(i) * p.pad_h) / static_cast<float>(p.H);  // coords_h (cmt_head.py:420)
-    const int units = p.D >> 3;  // 8-bin units per pixel
+    const int units = p.D / kBins;  // kBins-bin units per pixel
     const int items = p.W * units;
     const long long row_base = static_cast<long long>(blockIdx.x) * items;
+    constexpr int NV = kBins * 3;   // values per item
     for (int tl = threadIdx.x; tl < items; tl += blockDim.x) {
         const int j = tl / units;
-        const int k0 = (tl - j * units) << 3;
+        const int k0 = (tl - j * units) * kBins;
         const float u = utab[j];
-        float vals[24];
+        float vals[NV];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < kBins; ++kk) {
             const float d = dtab[k0 + kk];
             const float x0 = u * d, x1 = v * d;  // coords[..., :2] *= coords[..., 2:3]   (cmt_head.py:426)
 #pragma unroll
@@ -74,22 +77,34 @@ __global__ void __launch_bounds__(256) ray_pe_kernel(const float* __restrict__ i
                 vals[kk * 3 + c] = div_by_const(acc - p.pc_min[c], p.pc_rng[c], p.pc_inv[c]);  // (:431-432)
             }
         }
-        const long long t = row_base + tl;  // in 24-feature units
+        const long long t = row_base + tl;  // in NV-feature units
         if (kBf16) {
-            uint4* o = reinterpret_cast<uint4*>(out) + 3 * t;
+            if (kBins == 16) {
+                uint8_t* o = reinterpret_cast<uint8_t*>(out) + t * (NV * 2);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                uint4 w;
-                w.x = pack_bf16x2(vals[8 * q + 0], vals[8 * q + 1]);
-                w.y = pack_bf16x2(vals[8 * q + 2], vals[8 * q + 3]);
-                w.z = pack_bf16x2(vals[8 * q + 4], vals[8 * q + 5]);
-                w.w = pack_bf16x2(vals[8 * q + 6], vals[8 * q + 7]);
-                o[q] = w;
+                for (int q = 0; q < 3; ++q)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 32 * q),
+                                 "r"(pack_bf16x2(vals[16 * q + 0], vals[16 * q + 1])), "r"(pack_bf16x2(vals[16 * q + 2], vals[16 * q + 3])),
+                                 "r"(pack_bf16x2(vals[16 * q + 4], vals[16 * q + 5])), "r"(pack_bf16x2(vals[16 * q + 6], vals[16 * q + 7])),
+                                 "r"(pack_bf16x2(vals[16 * q + 8], vals[16 * q + 9])), "r"(pack_bf16x2(vals[16 * q + 10], vals[16 * q + 11])),
+                                 "r"(pack_bf16x2(vals[16 * q + 12], vals[16 * q + 13])), "r"(pack_bf16x2(vals[16 * q + 14], vals[16 * q + 15]))
+                                 : "memory");
+            } else {
+                uint4* o = reinterpret_cast<uint4*>(out) + 3 * t;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    uint4 w;
+                    w.x = pack_bf16x2(vals[8 * q + 0], vals[8 * q + 1]);
+                    w.y = pack_bf16x2(vals[8 * q + 2], vals[8 * q + 3]);
+                    w.z = pack_bf16x2(vals[8 * q + 4], vals[8 * q + 5]);
+                    w.w = pack_bf16x2(vals[8 * q + 6], vals[8 * q + 7]);
+                    o[q] = w;
+                }
             }
         } else {
-            float4* o = reinterpret_cast<float4*>(out) + 6 * t;
+            float4* o = reinterpret_cast<float4*>(out) + (NV / 4) * t;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) o[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+            for (int q = 0; q < NV / 4; ++q) o[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
         }
     }
 }
@@ -251,10 +266,13 @@ int launch_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, in
     const int grid = static_cast<int>(blocks);
     const size_t smem = static_cast<size_t>(D + W) * sizeof(float);
     CMT_CHECK_ARG(smem <= 48 * 1024, "cmt_ray_pe: W + D too large");
-    if (out_dtype == CMT_BF16)
-        ray_pe_kernel<true><<<grid, 256, smem, stream>>>(img2lidar, out, p);
+    const bool wide = D % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+    if (out_dtype == CMT_BF16 && wide)
+        ray_pe_kernel<true, 16><<<grid, 256, smem, stream>>>(img2lidar, out, p);
+    else if (out_dtype == CMT_BF16)
+        ray_pe_kernel<true, 8><<<grid, 256, smem, stream>>>(img2lidar, out, p);
     else
-        ray_pe_kernel<false><<<grid, 256, smem, stream>>>(img2lidar, out, p);
+        ray_pe_kernel<false, 8><<<grid, 256, smem, stream>>>(img2lidar, out, p);
     CMT_LAUNCH_CHECK("cmt_ray_pe");
     return CMT_OK;
 }

@@ -85,3 +85,6 @@ if which in ("gather", "all"):
 if which in ("raype", "all"):
     m = torch.eye(4, device=dev).repeat(B * 6, 1, 1).contiguous()
     timed("raype", lambda: ops.ray_pe(m, 40, 100, 64, 640.0, 1600.0, [-54, -54, -5, 54, 54, 3]))
+    # 64 frames (590 MB of bf16 output: beyond the 126 MB L2, so the time is an HBM write time)
+    m64 = torch.eye(4, device=dev).repeat(64 * 6, 1, 1).contiguous()
+    timed("raype_b64", lambda: ops.ray_pe(m64, 40, 100, 64, 640.0, 1600.0, [-54, -54, -5, 54, 54, 3]))
