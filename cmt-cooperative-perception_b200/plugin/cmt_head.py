@@ -300,9 +300,16 @@ class _CmtHeadBase(nn.Module):
     def _matrices(self, img_metas, device):
         """Host float64 inverse -> fp32 -> device, as cmt_head.py:428-429,441-444. [B,V,4,4] each."""
         l2i = np.stack([np.asarray(m["lidar2img"], dtype=np.float64) for m in img_metas])
-        i2l = np.linalg.inv(l2i)
-        both = torch.from_numpy(np.stack([l2i, i2l]).astype(np.float32)).to(device, non_blocking=True)
-        return both[0].contiguous(), both[1].contiguous()
+        # calibration rarely changes between frames: the inverse + upload (a host sync inside the path, SURVEY 8(f)
+        # rank 3) is done once per distinct set of matrices, keyed by their bytes
+        key = (l2i.shape, l2i.tobytes(), str(device))
+        hit = self._cache.get("mats")
+        if hit is None or hit[0] != key:
+            i2l = np.linalg.inv(l2i)
+            both = torch.from_numpy(np.stack([l2i, i2l]).astype(np.float32)).pin_memory().to(device, non_blocking=True)
+            hit = (key, (both[0].contiguous(), both[1].contiguous()))
+            self._cache["mats"] = hit
+        return hit[1]
 
     def _rv_pe(self, img_feats, img_metas, mats=None):
         """cmt_head.py:417-433 -> [B*V,H,W,C] fp32."""
