@@ -303,13 +303,16 @@ class _CmtHeadBase(nn.Module):
         # calibration rarely changes between frames: the inverse + upload (a host sync inside the path, SURVEY 8(f)
         # rank 3) is done once per distinct set of matrices, keyed by their bytes
         key = (l2i.shape, l2i.tobytes(), str(device))
-        hit = self._cache.get("mats")
-        if hit is None or hit[0] != key:
+        table = self._cache.setdefault("mats", {})   # a few entries: the cooperative heads alternate between two nodes
+        hit = table.get(key)
+        if hit is None:
             i2l = np.linalg.inv(l2i)
             both = torch.from_numpy(np.stack([l2i, i2l]).astype(np.float32)).pin_memory().to(device, non_blocking=True)
-            hit = (key, (both[0].contiguous(), both[1].contiguous()))
-            self._cache["mats"] = hit
-        return hit[1]
+            hit = (both[0].contiguous(), both[1].contiguous())
+            if len(table) >= 8:
+                table.pop(next(iter(table)))
+            table[key] = hit
+        return hit
 
     def _rv_pe(self, img_feats, img_metas, mats=None):
         """cmt_head.py:417-433 -> [B*V,H,W,C] fp32."""
