@@ -230,7 +230,11 @@ __global__ void __launch_bounds__(attndb::THREADS, 1)
 tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const TcAttnParams p) {
     using namespace attndb;
-    if (!kStatic && p.q_norm2 != nullptr && p.unsafe_flags[blockIdx.x] == 0) return;   // the static kernel took everything
+    pdl_trigger();
+    if (!kStatic && p.q_norm2 != nullptr) {
+        pdl_wait();                                    // the flags are the static kernel's output
+        if (p.unsafe_flags[blockIdx.x] == 0) return;   // the static kernel took everything
+    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -273,6 +277,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         fence_barrier_init();
     }
     if (warp == W_TMA) tmem_alloc(tmem_slot, 512);
+    pdl_wait();   // barrier init / TMEM allocation / descriptor prefetch overlapped the predecessor's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -618,6 +623,8 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long long G, void* o,
                                                             float* lse) {
     __shared__ int nseg_s;
+    pdl_trigger();
+    pdl_wait();
     const int QB = p.qblk;
     const int chunks = QB / 32;                       // blocks per item
     const int item = blockIdx.x / chunks;
@@ -802,23 +809,23 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     const bool masked = p.mask_bits != nullptr;
     if (p.q_norm2 != nullptr) {
         // static-shift kernel first (items with a score bound <= STATIC_LIMIT), then the online kernel for the rest
-        if (masked)
-            tc_attn_db_kernel<true, true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-        else
-            tc_attn_db_kernel<false, true><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        cudaError_t e = masked ? launch_pdl(tc_attn_db_kernel<true, true>, dim3(grid), dim3(attndb::THREADS), attndb::SMEM_BYTES, stream, tq, tk, tv, p)
+                               : launch_pdl(tc_attn_db_kernel<false, true>, dim3(grid), dim3(attndb::THREADS), attndb::SMEM_BYTES, stream, tq, tk, tv, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cmt_cross_attn_fwd(tcgen05, static shift) launch");
         CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05, static shift)");
     }
-    if (masked)
-        tc_attn_db_kernel<true, false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    else
-        tc_attn_db_kernel<false, false><<<grid, attndb::THREADS, attndb::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    {
+        cudaError_t e = masked ? launch_pdl(tc_attn_db_kernel<true, false>, dim3(grid), dim3(attndb::THREADS), attndb::SMEM_BYTES, stream, tq, tk, tv, p)
+                               : launch_pdl(tc_attn_db_kernel<false, false>, dim3(grid), dim3(attndb::THREADS), attndb::SMEM_BYTES, stream, tq, tk, tv, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cmt_cross_attn_fwd(tcgen05) launch");
+    }
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(tcgen05)");
     const long long mblocks = static_cast<long long>(a.B) * a.H * p.qblocks * (p.qblk / 32);
     CMT_CHECK_ARG(mblocks < (1ll << 31), "cmt_cross_attn_fwd: too many merge blocks");
     if (a.o_bf16)
-        tc_attn_merge_kernel<true><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, G, a.o, a.lse);
+        launch_pdl(tc_attn_merge_kernel<true>, dim3(static_cast<int>(mblocks)), dim3(256), 0, stream, p, G, a.o, a.lse);
     else
-        tc_attn_merge_kernel<false><<<static_cast<int>(mblocks), 256, 0, stream>>>(p, G, a.o, a.lse);
+        launch_pdl(tc_attn_merge_kernel<false>, dim3(static_cast<int>(mblocks)), dim3(256), 0, stream, p, G, a.o, a.lse);
     CMT_LAUNCH_CHECK("cmt_cross_attn_fwd(merge)");
     return CMT_OK;
 }

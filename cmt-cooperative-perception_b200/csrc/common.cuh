@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <cstdio>
 
@@ -92,6 +93,39 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(pred));
     return pred != 0;
+}
+
+// ------------------- programmatic dependent launch (PDL) -------------------
+// A kernel launched with launch_pdl() may begin (scheduling, barrier init, TMEM allocation, descriptor prefetch) while
+// its stream predecessor is still draining; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible, so it must precede every access to data a predecessor may write or still read.  Kernels call
+// pdl_trigger() first thing so that their own successor can be scheduled early.  Without the launch attribute both are
+// no-ops.  CMT_PDL=0 in the environment turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CMT_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------ mbarrier ----------------------------------

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const TcGemmParams p) {
     using namespace gemm;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* bias_s = reinterpret_cast<float*>(smem + RING_BYTES);
@@ -144,6 +145,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool bias_cached = p.bias != nullptr && !p.bias_per_row && p.N <= BIAS_CAP - 64;
     if (bias_cached)
         for (int i = threadIdx.x; i < BIAS_CAP; i += THREADS) bias_s[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
+    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch, bias cache: weights) overlapped the predecessor
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -574,7 +576,10 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
         p.b_resident = 1;
         grid = static_cast<int>(gm) * p.n_tiles;
     }
-    tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    {
+        cudaError_t e = launch_pdl(tc_gemm_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, stream, ta, tb, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cmt_gemm_bias_act(tcgen05) launch");
+    }
     CMT_LAUNCH_CHECK("cmt_gemm_bias_act(tcgen05)");
     return CMT_OK;
 }

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ add, void* __restrict__ ylp,
                                                             void* __restrict__ yadd) {
     constexpr int C = kPerLane * 32;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
@@ -119,10 +121,10 @@ int launch_add_layernorm(const float* x, const float* r, const float* gamma, con
     const long long cap = static_cast<long long>(device_sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     if (lp_dtype == CMT_BF16)
-        add_layernorm_kernel<8, true><<<static_cast<int>(blocks), 256, 0, stream>>>(x, r, gamma, beta, eps, M, y, gamma2,
+        launch_pdl(add_layernorm_kernel<8, true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, x, r, gamma, beta, eps, M, y, gamma2,
                                                                                    beta2, y2, add, ylp, yadd);
     else
-        add_layernorm_kernel<8, false><<<static_cast<int>(blocks), 256, 0, stream>>>(x, r, gamma, beta, eps, M, y, gamma2,
+        launch_pdl(add_layernorm_kernel<8, false>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, x, r, gamma, beta, eps, M, y, gamma2,
                                                                                     beta2, y2, add, ylp, yadd);
     CMT_LAUNCH_CHECK("cmt_add_layernorm");
     return CMT_OK;
