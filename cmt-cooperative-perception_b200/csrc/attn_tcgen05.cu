@@ -11,9 +11,12 @@
 // a second kernel merges the segments of each item.  The same partial/LSE algebra serves the multi-GPU KV-token
 // split (cmt_lse_merge).  The kernel layout is described at tc_attn_db_kernel below.
 //
-// Softmax is the online form with exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)) and a lazy
-// rescale: the running maximum is only raised (and O rescaled in TMEM) when it grows by more
-// than 2^8, so the common tile does no accumulator traffic at all.
+// Softmax uses exp2 (Q arrives pre-multiplied by log2(e)/sqrt(d)).  Two instantiations of the kernel:
+//   online  : running row maximum with a lazy rescale -- the maximum is only raised (and O rescaled in TMEM) when
+//             it grows by more than 2^8, so the common tile does no accumulator traffic at all;
+//   static  : when the caller passes the operand-norm maxima of the projections, |q.k| <= |q||k| bounds every score
+//             of a (frame, head); where the bound is <= 60 the weights 2^s need no shift at all (no row maximum, no
+//             subtraction, no rescale).  Items above the bound fall to the online kernel.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -132,9 +135,9 @@ __device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long l
 }
 
 // ------------------------------------------------------------------------------------------------
-// Double-buffered-S variant ("db").  The traces of the kernels above (tools/attn_trace.py) show that what
-// keeps the MUFU pipe from saturating is the round trip P stored -> issuer wakes -> PV + next S MMA ->
-// softmax wakes (~900 cycles even with a back-to-back issuer) sitting inside every warpgroup's chain.
+// Kernel layout ("db": double-buffered scores).  The event traces of the first schedules (tools/attn_trace.py)
+// showed that what keeps the MUFU pipe from saturating is the round trip P stored -> issuer wakes -> PV + next S MMA
+// -> softmax wakes (~900 cycles even with a back-to-back issuer) sitting inside every warpgroup's chain.
 // Here the KV tile is 64 tokens and every warpgroup owns TWO score buffers, so the scores of step j+1
 // (and j+2's, once PV(j) is issued) are already in TMEM while step j is being exponentiated: the
 // softmax warps never wait for the tensor pipe in steady state.
@@ -144,6 +147,7 @@ __device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long l
 //   512 threads: warps 0-11 softmax (one query row per thread, 64 scores in registers), 12 TMA + TMEM
 //   allocation, 13-15 one MMA issuer per warpgroup.  No setmaxnreg: 128 registers per thread are enough
 //   for 64-column tiles.
+
 // One thread = one 64-key tile of one frame: byte mask -> bit mask, tail beyond kv_end cleared.
 __global__ void pack_key_mask_kernel(const unsigned char* keep, unsigned long long* bits, int B, int N_kv, int kv_begin,
                                      int kv_end, int T) {

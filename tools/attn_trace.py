@@ -8,17 +8,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cmtcoop_b200 import ops, _lib
 lib = _lib.load()
 dev = "cuda:0"
-B, N_kv, L, H, Nq = 8, 56400, 1, 8, 900
+B, N_kv, L, H, Nq = 8, 56400, 1, 8, (int(sys.argv[3]) if len(sys.argv) > 3 else 900)
 STEPS, SL = 96, 16
 q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
 k = torch.randn(B, L, H, N_kv, 32, device=dev).bfloat16()
 vt = torch.randn(B, L, H, 32, N_kv, device=dev).bfloat16()
-ops.cross_attn(q, k, vt, 0); torch.cuda.synchronize()
+STATIC = len(sys.argv) > 4 and sys.argv[4] == "static"
+kw = {}
+if STATIC:   # operand norms -> static softmax shift kernel
+    kw = dict(q_norm2=q.float().view(B, Nq, H, 32).pow(2).sum(-1).amax(1).contiguous(),
+              k_norm2=k.float().pow(2).sum(-1).amax(-1).contiguous())
+ops.cross_attn(q, k, vt, 0, **kw); torch.cuda.synchronize()
 buf = torch.zeros(3 * STEPS * SL + 148, dtype=torch.int64, device=dev)
 lib.cmt_debug_attn_timing.argtypes = [ctypes.c_void_p]
 lib.cmt_debug_attn_timing(ctypes.c_void_p(buf.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); ops.cross_attn(q, k, vt, 0); e1.record(); torch.cuda.synchronize()
+e0.record(); ops.cross_attn(q, k, vt, 0, **kw); e1.record(); torch.cuda.synchronize()
 lib.cmt_debug_attn_timing(ctypes.c_void_p(0))
 cyc = buf[3 * STEPS * SL:].cpu().tolist()
 us = e0.elapsed_time(e1) * 1e3
