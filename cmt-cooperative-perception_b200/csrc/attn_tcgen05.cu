@@ -220,6 +220,9 @@ constexpr int DB_POLY = CMT_ATTN_DB_POLY;
 #endif
 constexpr int ST_POLY = CMT_ATTN_ST_POLY;
 constexpr float STATIC_LIMIT = 60.0f;
+#ifndef CMT_ATTN_LONE_POLY
+#define CMT_ATTN_LONE_POLY 2
+#endif
 }  // namespace attndb
 
 // kMask: key padding mask variant (the unmasked instantiation carries none of its code: even an untaken mask
@@ -481,7 +484,8 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             float m = -INFINITY, l = 0.0f;
 
             // One KV step of this thread's row.
-            auto step = [&](int jj) {
+            auto step = [&](auto poly_tag, int jj) {
+                constexpr int POLY = decltype(poly_tag)::value;   // one pair of exponentials in POLY on the FMA pipes
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
                 CMT_S_WAIT(&my_s_full[bsel], (g >> 1) & 1);
@@ -549,7 +553,6 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 // x - m and the row sums as packed fp32 pairs (FADD2): half the issue slots of scalar FADDs.
                 // One PAIR of exponentials in POLY runs on the FMA pipes (packed cubic) instead of the MUFU; without
                 // the row-max work there are issue slots for more of them.
-                constexpr int POLY = kStatic ? ST_POLY : DB_POLY;
                 const uint64_t neg_m2 = pack_f32x2(-m, -m);
                 uint64_t l2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
@@ -589,7 +592,16 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             // 2^s are normal numbers as they are: the softmax is shift-invariant, hence no row maximum, no subtraction
             // and no rescale of O; the partial's LSE is just log2 of the sum (m = 0).
             if (kStatic) m = 0.0f;
-            for (int jj = 0; jj < n; ++jj) step(jj);
+            // A tile with at most 32 queries (the 4-query tail of 900 = 7 * 128 + 4) has ONE active warp, and that warp
+            // shares its sub-partition's MUFU with the full tile next door: the pass is then bound by that one
+            // sub-partition (trace: 957 of 1165 cycles per step in the shared warp).  The lone warp therefore takes ALL
+            // its exponentials through the polynomial on the otherwise idle FMA pipes and leaves the MUFU to its neighbour.
+            const bool lone_warp = p.Nq - (qb * QBLK + wg * 128) <= 32;
+            if (lone_warp) {
+                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<int, CMT_ATTN_LONE_POLY>{}, jj);
+            } else {
+                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<int, (kStatic ? ST_POLY : DB_POLY)>{}, jj);
+            }
             // segment epilogue: normalised partial + log2-sum-exp into the workspace
             mbar_wait(&o_full[wg], seg & 1);
             ++seg;
@@ -695,8 +707,16 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, bool static_shif
     const int rows_last = Nq - (p->qblocks - 1) * p->qblk;
     // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
     // own chain, ~3/4 of that
-    p->w_full = static_shift ? 10 : 4;
-    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? (static_shift ? 7 : 3) : p->w_full;
+#ifndef CMT_ATTN_ST_WFULL
+#define CMT_ATTN_ST_WFULL 10
+#define CMT_ATTN_ST_WLAST 7
+#endif
+#ifndef CMT_ATTN_ON_WFULL
+#define CMT_ATTN_ON_WFULL 4
+#define CMT_ATTN_ON_WLAST 3
+#endif
+    p->w_full = static_shift ? CMT_ATTN_ST_WFULL : CMT_ATTN_ON_WFULL;
+    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? (static_shift ? CMT_ATTN_ST_WLAST : CMT_ATTN_ON_WLAST) : p->w_full;
     p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
     p->Wtot = static_cast<long long>(B) * H * p->Wg;
     // no more slots than full-weight steps, so that a range is never shorter than the widest step
