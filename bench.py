@@ -184,6 +184,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--kv-split", action="store_true",
+                    help="BASELINE configs[4] variant: every rank sees the SAME frames and attends 1/N of the K/V tokens; "
+                         "one NCCL all-gather of (O, LSE) per decoder layer + log-sum-exp merge (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,11 +211,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
-    kind, cfg, inputs = build_case(args.workload, B, seed=rank)
+    kv_split = args.kv_split and world > 1
+    if kv_split:
+        args.no_cuda_graph = True   # the per-layer NCCL all-gather stays outside graph capture
+    kind, cfg, inputs = build_case(args.workload, B, seed=0 if kv_split else rank)
     head = build_head({k: v for k, v in cfg.items() if not k.startswith("_")})
     synth.load_synth_weights(head, 0)
     head = head.to(dev).eval().set_precision("bf16")
     head.apply_shared_conv = False
+    if kv_split:
+        head.transformer.enable_kv_split()
     coop = kind.endswith("Coop")
     feat_keys = [k for k, v in inputs.items() if isinstance(v, np.ndarray)]
     host = {k: torch.from_numpy(inputs[k]).pin_memory() for k in feat_keys}
@@ -286,7 +294,7 @@ def main():
         ms_e2e = float(ms_t.item())
         h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
 
-    frames = B * world * args.steps
+    frames = B * (1 if kv_split else world) * args.steps
     value = frames / (ms * 1e-3)
     pk = peaks()
     # roofline of the dominant kernel (tc_attn_kernel): algorithmic flops 4*Nq*N_kv*C per frame per layer
@@ -318,10 +326,14 @@ def main():
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_sample(args.workload)
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if kv_split else "weak",
+                    vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload=WORKLOADS[args.workload][3], frames_per_gpu=B, global_batch=B * world,
-                                parallelism=f"frame sharding x{world}, no data-path collective",
+                    config=dict(workload=WORKLOADS[args.workload][3], frames_per_gpu=B,
+                                global_batch=B if kv_split else B * world,
+                                parallelism=(f"K/V tokens split x{world}: queries replicated, one NCCL all-gather of "
+                                             "(O, LSE) per decoder layer + LSE merge" if kv_split else
+                                             f"frame sharding x{world}, no data-path collective"),
                                 l2="inputs (%.0f MB per step) exceed the 126 MB L2" % (h2d / 1e6),
                                 scope="forward_single from post-shared_conv BEV map + image features to task-head outputs",
                                 cuda_graph=not args.no_cuda_graph, eager_ms_per_step=ms_eager / args.steps),
