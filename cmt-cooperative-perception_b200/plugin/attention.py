@@ -174,13 +174,15 @@ class FlashMHA(nn.Module):
         all-gather over NVLink (NCCL) -> log-sum-exp merge.  Queries are replicated."""
         return self._merge_kv_split(self.project_q(q), cache, layer)
 
-    def _merge_kv_split(self, qp, cache: KVCache, layer: int):
-        """qp: already projected + pre-scaled queries [B,Nq,E]."""
+    def _merge_kv_split(self, qp, cache: KVCache, layer: int, q_norm2=None):
+        """qp: already projected + pre-scaled queries [B,Nq,E]; q_norm2: optional [B,H] query norm maxima (with
+        cache.k_norm2, the maxima over THIS rank's keys, they select the static-shift kernel for the local partial)."""
         from .. import parallel
         B, Nq, E = qp.shape
         q = qp
         if cache.n_kv > 0:
-            o_part, lse = ops.cross_attn(qp, cache.k, cache.vt, layer, return_lse=True, o_dtype=torch.float32)
+            o_part, lse = ops.cross_attn(qp, cache.k, cache.vt, layer, return_lse=True, o_dtype=torch.float32,
+                                         q_norm2=q_norm2, k_norm2=cache.k_norm2 if q_norm2 is not None else None)
         else:  # this rank holds no tokens: neutral element of the merge
             o_part = torch.zeros((B, Nq, E), dtype=torch.float32, device=q.device)
             lse = torch.full((B, self.num_heads, Nq), float("-inf"), dtype=torch.float32, device=q.device)

@@ -95,8 +95,9 @@ class _CmtTransformerBase(nn.Module):
             if hi <= lo:
                 return KVCache(None, None, 0, group), xv
             xk_l, xv_l = xk[:, lo:hi].contiguous(), xv[:, lo:hi].contiguous()
-            return KVCache(ops.project_keys(xk_l, wk, bk, L, H), ops.project_values_t(xv_l, wv, bv, L, H),
-                           hi - lo, group), xv
+            kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
+            return KVCache(ops.project_keys(xk_l, wk, bk, L, H, norm2_max=kn2), ops.project_values_t(xv_l, wv, bv, L, H),
+                           hi - lo, group, k_norm2=kn2), xv
         kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
         k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)
         vt = ops.project_values_t(xv, wv, bv, L, H)

@@ -103,7 +103,7 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
 
     # max |q|^2 per (layer, frame, head) of the cross-attention queries: with cache.k_norm2 the attention kernel gets a
     # bound on every score and drops the running row maximum (ops.cross_attn)
-    static_shift = cache.group is None and cache.k_norm2 is not None and dt == torch.bfloat16
+    static_shift = cache.k_norm2 is not None and dt == torch.bfloat16
     qn2 = torch.zeros((L, B, H), dtype=torch.float32, device=dev) if static_shift else None
 
     for li, layer in enumerate(decoder.layers):
@@ -121,7 +121,10 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
         cw = mha.compute_weights()
         if static_shift:
             qc = ops.project_queries(x1q_lp, cw["wq"], cw["bq"], H, _Q_SCALE, norm2_max=qn2[li])
-            ctx = ops.cross_attn(qc, cache.k, cache.vt, li, q_norm2=qn2[li], k_norm2=cache.k_norm2)
+            if cache.group is None:
+                ctx = ops.cross_attn(qc, cache.k, cache.vt, li, q_norm2=qn2[li], k_norm2=cache.k_norm2)
+            else:
+                ctx = mha._merge_kv_split(qc, cache, li, q_norm2=qn2[li])
         elif cache.group is None:
             qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
             ctx = ops.cross_attn(qc, cache.k, cache.vt, li)
