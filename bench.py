@@ -46,9 +46,10 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of tc_attn_db_kernel per launch from the committed ncu --set full
-# capture (profiles/r1_attn_db_n3s_ncu_raw.csv: 1.3963 GB + 0.0113 GB at B=8), per frame.  K+V of one layer are
+# capture (profiles/r1_attn_static_ncu_raw.csv, the static-shift instantiation the bench runs: 1.3950 GB + 0.0118 GB at B=8),
+# per frame.  K+V of one layer are
 # 57.8 MB per frame; the 3 query blocks of a (frame, head) stream them at different times, hence ~3x.
-NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.396296e9 + 0.011308e9) / 8}
+NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.394999e9 + 0.011791e9) / 8}
 
 
 def build_case(workload, B, seed=0):

@@ -1,5 +1,5 @@
 """Launch each hot kernel a few times at the nuScenes-multimodal shape (B=8) for an ncu capture.
-usage: python tools/prof_kernels.py [kproj|vproj|mlp1|mlp2|attn|attnonly|gather|raype|all]"""
+usage: python tools/prof_kernels.py [kproj|vproj|mlp1|mlp2|attn|attnonly|attnstatic|gather|raype|all]"""
 import os
 import sys
 
@@ -64,6 +64,13 @@ if which == "attnonly":   # attention alone on random K / V^T (A/B runs of kerne
     cyc = buf[3 * 96 * 16:].cpu().tolist()
     us = e0.elapsed_time(e1) * 1e3
     print(f"cycles/CTA median {sorted(cyc)[74]} max {max(cyc)}; {us:.0f} us -> SM clock >= {max(cyc) / us / 1e3:.3f} GHz", flush=True)
+if which == "attnstatic":   # only static-shift attention launches (ncu capture of the shipped bench kernel)
+    k = torch.randn(B, 1, H, N_kv, 32, device=dev).bfloat16()
+    vt = torch.randn(B, 1, H, 32, N_kv, device=dev).bfloat16()
+    q = (torch.randn(B, Nq, 256, device=dev) * 0.25).bfloat16()
+    qn2 = q.float().view(B, Nq, H, 32).pow(2).sum(-1).amax(1).contiguous()
+    kn2 = k.float().pow(2).sum(-1).amax(-1).contiguous()
+    timed("attn_static", lambda: ops.cross_attn(q, k, vt, 0, q_norm2=qn2, k_norm2=kn2))
 if which in ("mlp1", "mlp2", "all"):
     M = 8 * 6 * 4000
     a = torch.randn(M, 192, device=dev).bfloat16()
