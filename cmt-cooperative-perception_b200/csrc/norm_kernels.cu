@@ -135,18 +135,14 @@ int launch_add_layernorm(const float* x, const float* r, const float* gamma, con
 // grouped 1x1 conv (a per-decoder-layer GEMM, h = x W1^T), every (layer, query row, output head) needs
 //   y = ReLU(LN_64(h) * gamma + beta),   out[o] = y . w2[o] + b2[o]        (o < c_out <= CMAX)
 // Eager torch runs this as ~10 elementwise / reduction passes over the 66 MB h tensor plus an einsum (0.45 ms per
-// forward at B = 8); here one warp owns a (layer, row): per head a coalesced 256-byte read, two shuffle reductions for
-// the statistics, the affine + ReLU in registers and CMAX 64-long dot products against w2 held in shared memory.
-// fp32 throughout (these outputs feed the top-k).
+// forward at B = 8).  Here one THREAD owns a (layer, row): per output head it pulls the 64 hidden values into
+// registers (sixteen 16-byte loads of its own 256 contiguous bytes), takes the statistics and the affine + ReLU in
+// registers, and runs the CMAX 64-long dot products against w2 held in shared memory (all lanes of a warp read the same
+// weight: broadcast).  No shuffles (a warp-per-row version spent its time in 70 shuffles per head: 146 us), fp32
+// throughout (these outputs feed the top-k).
 constexpr int TH_HC = 64;   // hidden channels per head (head_conv = 64 in every reference config)
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__global__ void __launch_bounds__(256) task_head_tail_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) task_head_tail_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ w2,
                                                              const float* __restrict__ b2, float* __restrict__ out, int M,
                                                              int NH, int CMAX, float eps) {
@@ -163,40 +159,49 @@ __global__ void __launch_bounds__(256) task_head_tail_kernel(const float* __rest
     }
     for (int i = threadIdx.x; i < NH * CMAX; i += blockDim.x) b2s[i] = b2[l * NH * CMAX + i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int m = blockIdx.x * nwarp + warp; m < M; m += gridDim.x * nwarp) {
-        const float* hrow = h + (static_cast<long long>(l) * M + m) * NH * TH_HC;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        const float4* hrow = reinterpret_cast<const float4*>(h + (static_cast<long long>(l) * M + m) * NH * TH_HC);
         float* orow = out + (static_cast<long long>(l) * M + m) * NH * CMAX;
         for (int hd = 0; hd < NH; ++hd) {
-            const float2 v = *reinterpret_cast<const float2*>(hrow + hd * TH_HC + 2 * lane);
-            const float mu = warp_sum(v.x + v.y) * (1.0f / TH_HC);
-            const float d0 = v.x - mu, d1 = v.y - mu;
-            const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / TH_HC);
-            const float sd = sqrtf(var + eps);
-            const float2 g = *reinterpret_cast<const float2*>(gs + hd * TH_HC + 2 * lane);
-            const float2 b = *reinterpret_cast<const float2*>(bs + hd * TH_HC + 2 * lane);
-            const float y0 = fmaxf(d0 / sd * g.x + b.x, 0.0f), y1 = fmaxf(d1 / sd * g.y + b.y, 0.0f);
-            // the CMAX dot products: partial sums of four outputs at a time go through the butterfly together (the
-            // shuffles of one reduction are a dependent chain; four interleaved chains keep the warp issuing)
-            float mine = 0.0f;   // lane o keeps output o
-            for (int o0 = 0; o0 < CMAX; o0 += 4) {
-                float acc[4];
+            float y[TH_HC];
+            float sum = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int o = min(o0 + j, CMAX - 1);
-                    const float2 w = *reinterpret_cast<const float2*>(w2s + (hd * CMAX + o) * TH_HC + 2 * lane);
-                    acc[j] = y0 * w.x + y1 * w.y;
-                }
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], sft);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (lane == o0 + j) mine = acc[j];
+            for (int i = 0; i < TH_HC / 4; ++i) {
+                const float4 v = __ldg(hrow + hd * (TH_HC / 4) + i);
+                y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
+                sum += (v.x + v.y) + (v.z + v.w);
             }
-            if (lane < CMAX) orow[hd * CMAX + lane] = mine + b2s[hd * CMAX + lane];
+            const float mu = sum * (1.0f / TH_HC);
+            float sq = 0.0f;
+#pragma unroll
+            for (int c = 0; c < TH_HC; ++c) {
+                y[c] -= mu;
+                sq = fmaf(y[c], y[c], sq);
+            }
+            const float sd = sqrtf(sq * (1.0f / TH_HC) + eps);
+            const float4* g4 = reinterpret_cast<const float4*>(gs + hd * TH_HC);
+            const float4* b4 = reinterpret_cast<const float4*>(bs + hd * TH_HC);
+#pragma unroll
+            for (int i = 0; i < TH_HC / 4; ++i) {
+                const float4 g = g4[i], b = b4[i];
+                y[4 * i] = fmaxf(y[4 * i] / sd * g.x + b.x, 0.0f);
+                y[4 * i + 1] = fmaxf(y[4 * i + 1] / sd * g.y + b.y, 0.0f);
+                y[4 * i + 2] = fmaxf(y[4 * i + 2] / sd * g.z + b.z, 0.0f);
+                y[4 * i + 3] = fmaxf(y[4 * i + 3] / sd * g.w + b.w, 0.0f);
+            }
+            for (int o = 0; o < CMAX; ++o) {
+                const float4* w4 = reinterpret_cast<const float4*>(w2s + (hd * CMAX + o) * TH_HC);
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < TH_HC / 4; ++i) {
+                    const float4 w = w4[i];
+                    a0 = fmaf(y[4 * i], w.x, a0);
+                    a1 = fmaf(y[4 * i + 1], w.y, a1);
+                    a2 = fmaf(y[4 * i + 2], w.z, a2);
+                    a3 = fmaf(y[4 * i + 3], w.w, a3);
+                }
+                orow[hd * CMAX + o] = (a0 + a1) + (a2 + a3) + b2s[hd * CMAX + o];
+            }
         }
     }
 }
@@ -212,10 +217,8 @@ int launch_task_head_tail(const float* h, const float* gamma, const float* beta,
         cudaError_t e = cudaFuncSetAttribute(task_head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(task_head_tail)");
     }
-    int bx = (M + 7) / 8;
-    const int cap = device_sm_count() * 4 / (L > 0 ? L : 1) + 1;
-    if (bx > cap) bx = cap;
-    task_head_tail_kernel<<<dim3(bx, L), 256, smem, stream>>>(h, gamma, beta, w2, b2, out, M, NH, CMAX, eps);
+    int bx = (M + 127) / 128;
+    task_head_tail_kernel<<<dim3(bx, L), 128, smem, stream>>>(h, gamma, beta, w2, b2, out, M, NH, CMAX, eps);
     CMT_LAUNCH_CHECK("cmt_task_head_tail");
     return CMT_OK;
 }
