@@ -117,3 +117,24 @@ def test_synth_is_deterministic():
     b = synth.synth_tensor("transformer.decoder.layers.0.attentions.1.attn.in_proj_weight", (768, 256), 0)
     assert np.array_equal(a, b) and a.dtype == np.float32
     assert abs(float(a[0, 0]) - float(a[0, 0])) == 0 and float(np.abs(a).max()) <= np.sqrt(6.0 / (256 + 768)) + 1e-7
+
+
+def test_graph_runner_calibration_key():
+    """runtime._metas_key: a CUDA graph bakes the calibration in, so the key must change exactly when lidar2img (of any
+    node prefix) or the pad shape changes, and ignore everything else in img_metas."""
+    import numpy as np
+    from cmtcoop_b200.runtime import _metas_key
+    rng = np.random.RandomState(0)
+    m = [dict(lidar2img=[rng.randn(4, 4) for _ in range(3)], pad_shape=[(640, 1600, 3)] * 3, sample_idx="a"),
+         dict(lidar2img=[rng.randn(4, 4) for _ in range(3)], pad_shape=[(640, 1600, 3)] * 3, sample_idx="b")]
+    k0 = _metas_key(m)
+    same = [dict(d, sample_idx="other", box_type_3d=object) for d in m]
+    assert _metas_key(same) == k0
+    moved = [dict(d) for d in m]
+    moved[1] = dict(moved[1], lidar2img=[x + (1e-9 if i == 2 else 0.0) for i, x in enumerate(m[1]["lidar2img"])])
+    assert _metas_key(moved) != k0
+    padded = [dict(d, pad_shape=[(672, 1600, 3)] * 3) for d in m]
+    assert _metas_key(padded) != k0
+    coop = [dict(vehicle_lidar2img=[np.eye(4)], infrastructure_lidar2img=[np.eye(4)] * 3)]
+    coop2 = [dict(vehicle_lidar2img=[np.eye(4)], infrastructure_lidar2img=[np.eye(4)] * 2 + [2 * np.eye(4)])]
+    assert _metas_key(coop) != _metas_key(coop2)
