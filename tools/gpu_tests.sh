@@ -13,3 +13,5 @@ run simple tests/test_gpu_kernels.py -k "not gemm and not attention"
 run gemm tests/test_gpu_kernels.py -k "gemm"
 run attn tests/test_gpu_kernels.py -k "attention"
 run heads tests/test_gpu_heads.py
+run decoder tests/test_gpu_decoder.py
+run multi tests/test_gpu_multi.py
