@@ -261,9 +261,21 @@ def main():
         sampler = ClockSampler(local_rank)
         sampler.start()
         n0 = ops.launch_count()
+        # per-CTA clock64 totals of the attention kernel (one 8-byte store per CTA): with the event time of the same launch
+        # they give the SM clock the kernel actually ran at -- NVML keeps reporting the maximum clock while the kernel
+        # runs power-limited, and the MUFU-floor analysis in DESIGN.md is in cycles
+        import ctypes
+        from cmtcoop_b200 import _lib
+        lib = _lib.load()
+        lib.cmt_debug_attn_timing.argtypes = [ctypes.c_void_p]
+        tbuf = torch.zeros(3 * 96 * 16 + 148, dtype=torch.int64, device=dev)
+        lib.cmt_debug_attn_timing(ctypes.c_void_p(tbuf.data_ptr()))
         ops.profile_events("cross_attn", True)
         ms_eager = timed(lambda: forward(resident), args.steps)
         attn_ms = ops.profile_events("cross_attn", False)
+        lib.cmt_debug_attn_timing(ctypes.c_void_p(0))
+        cyc = float(tbuf[3 * 96 * 16:].max().item())   # the last cross-attention launch of the timed region
+        sm_clock_ghz = cyc / (attn_ms[-1] * 1e-3) / 1e9 if attn_ms and cyc > 0 else None
         launches = ops.launch_count() - n0
         ms = ms_eager
         if not args.no_cuda_graph:
@@ -319,6 +331,7 @@ def main():
                     peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"],
                     traffic=NCU_DRAM_BYTES_PER_FRAME.get(args.workload, 0) * B or None, peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
                     launches_timed=len(attn_ms), avg_launch_ms=attn_avg_ms,
+                    sm_clock_ghz_under_kernel=sm_clock_ghz,
                     share_of_step=attn_avg_ms * len(attn_ms) / ms_eager,
                     algorithmic_flops_per_launch=flops_per_launch)
 
