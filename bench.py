@@ -175,6 +175,40 @@ def cpu_baseline_sample(workload):
 
 
 # ---------------------------------------------------------------------------------------------
+FEAT_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
+# ops.profile_events tags timed per launch inside the eager timed region (CUDA events on the launching stream)
+KERNEL_TAGS = ("cross_attn", "ray_pe", "gather_tokens", "k_proj", "v_proj", "rv_pe_mlp.0", "rv_pe_mlp.2")
+
+
+def frame0_inputs(inputs, B, coop, feat_dtype):
+    """Frame 0 of the step's batch as an oracle input dict.  Features are the values the GPU path received
+    (rounded to the hand-over dtype), as fp32 numpy."""
+    out = dict(img_metas=inputs["img_metas"][:1])
+    for k, v in inputs.items():
+        if isinstance(v, np.ndarray):
+            per = v.shape[0] // B
+            t = torch.from_numpy(v[:per]).to(feat_dtype).float()
+            out[k] = t.numpy()
+        elif k != "img_metas":
+            out[k] = v
+    return out
+
+
+def parity_check(cfg, inputs, B, coop, feat_dtype, head, rets):
+    """Frame 0 of the timed workload against the CPU oracle (outside every timed region)."""
+    from oracle import cmt_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    with torch.no_grad():
+        want, _ = O.head_forward(sd, cfg, frame0_inputs(inputs, B, coop, feat_dtype))
+    per = {n: O.rel_l2(rets[0][n][:, :1].float().cpu(), want[0][n]) for n in want[0]}
+    worst = max(per.values())
+    shp = {n: list(want[0][n].shape) for n in ("cls_logits", "center")}
+    return dict(rel_l2=worst, per_output=per, tolerance=1e-2, ok=bool(worst < 1e-2),
+                checked_shape=f"frame 0 of the timed batch, all 6 decoder layers: cls_logits {shp['cls_logits']}, "
+                              f"center {shp['center']} (+ height, dim, rot, vel) vs the fp32 CPU oracle on the same inputs")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,7 +217,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="nusc", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--feat-dtype", default="bf16", choices=sorted(FEAT_DTYPES),
+                    help="dtype in which the neck's feature maps are handed over (host buffers of the e2e leg, resident "
+                         "buffers of the device leg); the gather kernel rounds fp32 features to bf16 on arrival, so the "
+                         "outputs are bit-identical for fp32 and bf16 hand-over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the frame-0 oracle comparison (about 2 s of host work)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--kv-split", action="store_true",
                     help="BASELINE configs[4] variant: every rank sees the SAME frames and attends 1/N of the K/V tokens; "
@@ -204,7 +243,8 @@ def main():
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     import torch.distributed as dist
     from cmtcoop_b200 import ops
-    from cmtcoop_b200.plugin import build_head
+    from cmtcoop_b200.plugin import build_head, fused_decoder
+    from cmtcoop_b200.runtime import GraphedForward, PipelinedRunner, numa_local_to_gpu
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -212,6 +252,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
+    fdt = FEAT_DTYPES[args.feat_dtype]
     kv_split = args.kv_split and world > 1
     if kv_split:
         args.no_cuda_graph = True   # the per-layer NCCL all-gather stays outside graph capture
@@ -224,7 +265,9 @@ def main():
         head.transformer.enable_kv_split()
     coop = kind.endswith("Coop")
     feat_keys = [k for k, v in inputs.items() if isinstance(v, np.ndarray)]
-    host = {k: torch.from_numpy(inputs[k]).pin_memory() for k in feat_keys}
+    with numa_local_to_gpu(local_rank) as numa:
+        # pinned staging buffers first-touched on the GPU's own NUMA node
+        host = {k: torch.from_numpy(inputs[k]).to(fdt).pin_memory() for k in feat_keys}
     resident = {k: v.to(dev) for k, v in host.items()}
     metas = inputs["img_metas"]
 
@@ -257,41 +300,65 @@ def main():
     with torch.no_grad():
         # ---- device-resident throughput ----
         for _ in range(args.warmup):
-            forward(resident)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        n0 = ops.launch_count()
-        # per-CTA clock64 totals of the attention kernel (one 8-byte store per CTA): with the event time of the same launch
-        # they give the SM clock the kernel actually ran at -- NVML keeps reporting the maximum clock while the kernel
-        # runs power-limited, and the MUFU-floor analysis in DESIGN.md is in cycles
+            rets = forward(resident)
+        # diagnostic pass, OUTSIDE the timed region: per-CTA clock64 totals of the attention kernel (one 8-byte store per
+        # CTA) with the event time of the same launch give the SM clock the kernel really ran at -- NVML keeps reporting
+        # the maximum clock while the kernel runs power-limited, and the MUFU-floor analysis in DESIGN.md is in cycles
         import ctypes
         from cmtcoop_b200 import _lib
         lib = _lib.load()
-        lib.cmt_debug_attn_timing.argtypes = [ctypes.c_void_p]
         tbuf = torch.zeros(3 * 96 * 16 + 148, dtype=torch.int64, device=dev)
         lib.cmt_debug_attn_timing(ctypes.c_void_p(tbuf.data_ptr()))
         ops.profile_events("cross_attn", True)
-        ms_eager = timed(lambda: forward(resident), args.steps)
-        attn_ms = ops.profile_events("cross_attn", False)
+        forward(resident)
+        diag_ms = ops.profile_events("cross_attn", False)
         lib.cmt_debug_attn_timing(ctypes.c_void_p(0))
-        cyc = float(tbuf[3 * 96 * 16:].max().item())   # the last cross-attention launch of the timed region
-        sm_clock_ghz = cyc / (attn_ms[-1] * 1e-3) / 1e9 if attn_ms and cyc > 0 else None
+        cyc = float(tbuf[3 * 96 * 16:].max().item())   # the last cross-attention launch of the pass
+        sm_clock_ghz = cyc / (diag_ms[-1] * 1e-3) / 1e9 if diag_ms and cyc > 0 else None
+        # which instantiation do the attention items take?  (static shift iff the operand-norm score bound <= 60)
+        static_frac = None
+        if fused_decoder.last_norms is not None:
+            qn2, kn2 = fused_decoder.last_norms
+            bound = torch.sqrt(qn2 * kn2.permute(1, 0, 2)) * 1.0079 + 1e-3
+            static_frac = float((bound <= 60.0).float().mean().item())
+
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n0 = ops.launch_count()
+        for t in KERNEL_TAGS:
+            ops.profile_events(t, True)
+        ms_eager = timed(lambda: forward(resident), args.steps)
+        per_launch = {t: ops.profile_events(t, False) for t in KERNEL_TAGS}
+        attn_ms = per_launch["cross_attn"]
         launches = ops.launch_count() - n0
         ms = ms_eager
+        # the online-softmax instantiation on the same workload (what a checkpoint with peaky logits would run):
+        # per-launch device time only, not part of `value`
+        ops.FORCE_ONLINE_SOFTMAX = True
+        for _ in range(2):
+            forward(resident)
+        ops.profile_events("cross_attn", True)
+        for _ in range(3):
+            forward(resident)
+        online_ms = ops.profile_events("cross_attn", False)
+        ops.FORCE_ONLINE_SOFTMAX = False
+        rets = forward(resident)
         if not args.no_cuda_graph:
             # same forward, same kernels, replayed from a CUDA graph (public API: cmtcoop_b200.runtime.GraphedForward):
-            # the eager run above keeps the per-launch attention timings for the roofline
-            from cmtcoop_b200.runtime import GraphedForward
+            # the eager run above keeps the per-launch kernel timings for the roofline
             graphed = GraphedForward(head, metas, resident, adopt_inputs=True)
             for _ in range(3):
-                graphed()
+                rets = graphed()
             ms = timed(lambda: graphed(), args.steps)
         clocks = sampler.stop()
+        torch.cuda.synchronize()
+        parity = None
+        if rank == 0 and not args.no_parity:
+            parity = parity_check(cfg, inputs, B, coop, fdt, head, rets)
 
         # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of every task-head tensor ----
         # public serving API: cmtcoop_b200.runtime.PipelinedRunner double-buffers the H2D of step i+1 and
         # the D2H of step i-1 under the compute of step i; every byte still moves inside the timed region
-        from cmtcoop_b200.runtime import PipelinedRunner
         runner = PipelinedRunner(head, metas, host, dev, use_cuda_graph=not args.no_cuda_graph)
         runner.run([host] * 3)
         torch.cuda.synchronize()
@@ -310,30 +377,80 @@ def main():
     frames = B * (1 if kv_split else world) * args.steps
     value = frames / (ms * 1e-3)
     pk = peaks()
-    # roofline of the dominant kernel (tc_attn_kernel): algorithmic flops 4*Nq*N_kv*C per frame per layer
+
     def node_tokens(prefix):
-        n = 0
+        n_b = n_i = 0
         p, i = inputs.get(prefix + "pts_feats"), inputs.get(prefix + "img_feats")
         if p is not None:
-            n += p.shape[2] * p.shape[3]
+            n_b = p.shape[2] * p.shape[3]
         if i is not None:
-            n += (i.shape[0] // B) * i.shape[2] * i.shape[3]
-        return n
+            n_i = (i.shape[0] // B) * i.shape[2] * i.shape[3]
+        return n_b, n_i
 
-    kv_per_node = [node_tokens("vehicle_"), node_tokens("infrastructure_")] if coop else [node_tokens("")]
-    N_kv = float(np.mean(kv_per_node))  # one attention launch per node per layer
-    flops_per_launch = 4.0 * 900 * N_kv * 256 * B
+    nodes = [node_tokens("vehicle_"), node_tokens("infrastructure_")] if coop else [node_tokens("")]
+    N_kv = float(np.mean([a + b for a, b in nodes]))  # one attention launch per node per layer
+    N_img = float(np.mean([b for _, b in nodes]))
+    N_kv_rank = N_kv
+    if kv_split:
+        from cmtcoop_b200 import parallel
+        lo, hi = parallel.kv_split_range(int(N_kv), rank, world)
+        N_kv_rank = float(hi - lo)   # each rank attends its own share of the tokens
+    # roofline of the dominant kernel (tc_attn_db_kernel): algorithmic flops 4*Nq*N_kv*C per frame per layer
+    flops_per_launch = 4.0 * 900 * N_kv_rank * 256 * B
     attn_avg_ms = float(np.mean(attn_ms)) if attn_ms else None
     roof = None
+    kernels = []
+    fsz = torch.empty((), dtype=fdt).element_size()
     if attn_avg_ms:
         achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="tc_attn_db_kernel<static shift> (+ online-kernel early exit + merge)", achieved=achieved,
-                    peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_tflops_sustained"],
-                    traffic=NCU_DRAM_BYTES_PER_FRAME.get(args.workload, 0) * B or None, peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
+        exps = 900.0 * N_kv_rank * 8 * B            # one exponential per (query, key, head)
+        poly = (1.0 / 3.0) if (static_frac or 0) > 0.5 else 0.2   # share of the exponentials on the FMA pipes (ST_POLY / DB_POLY)
+        clk = sm_clock_ghz or 1.9
+        floor_ms = exps * (1.0 - poly) / (16.0 * 148 * clk * 1e9) * 1e3
+        online_avg = float(np.mean(online_ms)) if online_ms else None
+        roof = dict(bound="tensor", kernel="tc_attn_db_kernel<static shift> (+ online-kernel early exit + merge)",
+                    achieved=achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=achieved / pk["bf16_tflops_sustained"],
+                    traffic=NCU_DRAM_BYTES_PER_FRAME.get(args.workload, 0) * B or None,
+                    traffic_source="profiles/ ncu --set full capture of this kernel at this shape (not measured in this run)",
+                    peak_source=pk["source"] + " sustained bf16 (kernel timed inside the step)",
                     launches_timed=len(attn_ms), avg_launch_ms=attn_avg_ms,
                     sm_clock_ghz_under_kernel=sm_clock_ghz,
                     share_of_step=attn_avg_ms * len(attn_ms) / ms_eager,
-                    algorithmic_flops_per_launch=flops_per_launch)
+                    algorithmic_flops_per_launch=flops_per_launch,
+                    static_item_fraction=static_frac,
+                    online_kernel=dict(avg_launch_ms=online_avg,
+                                       frac=(flops_per_launch / (online_avg * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]) if online_avg else None,
+                                       note="same workload with the operand-norm bound ignored: every item on the online-softmax "
+                                            "instantiation (what a checkpoint with a score bound > 60 runs)"),
+                    exp_roofline=dict(exponentials_per_launch=exps, mufu_ex2_per_clk_per_sm=16, sms=148,
+                                      polynomial_share=poly, sm_clock_ghz=clk, floor_ms=floor_ms,
+                                      frac=floor_ms / attn_avg_ms,
+                                      note="time the MUFU pipe alone needs for the exponentials not taken by the FMA-pipe "
+                                           "polynomial, over the measured launch time: at d_head = 32 the softmax pipe, not the "
+                                           "tensor pipe, is the first wall (128 MMA flops per exponential)"))
+
+        def kline(tag, kernel, bound, work, unit_peak, note=None):
+            t = per_launch.get(tag) or []
+            if not t:
+                return
+            avg = float(np.mean(t))
+            ach = work / (avg * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            kernels.append(dict(kernel=kernel, tag=tag, bound=bound, avg_launch_ms=avg, launches_timed=len(t), achieved=ach,
+                                peak=unit_peak, unit="GB/s" if bound == "hbm" else "TFLOP/s", frac=ach / unit_peak,
+                                algorithmic_work_per_launch=work, share_of_step=avg * len(t) / ms_eager, **({"note": note} if note else {})))
+
+        n_nodes = len(nodes)
+        hb, tp = pk["hbm_gbs"], pk["bf16_tflops_sustained"]
+        kline("ray_pe", "ray_pe_kernel (K1)", "hbm", B * N_img * 192 * 2.0, hb,
+              note="at 8 frames the 74 MB output is L2-resident and the launch is ~20 us; profiles/ holds the 64-frame run")
+        kline("gather_tokens", "gather_tokens_kernel (K4)", "hbm",
+              B * N_kv * 256 * fsz + B * N_img * 256 * 4 + (N_kv - N_img) * 256 * 4 + 2 * B * N_kv_rank * 256 * 2, hb)
+        kline("k_proj", "tc_gemm_kernel K projection, all layers", "tensor", 2.0 * B * N_kv_rank * 256 * 1536, tp)
+        kline("v_proj", "tc_gemm_kernel V^T projection, all layers", "tensor", 2.0 * B * N_kv_rank * 256 * 1536, tp)
+        kline("rv_pe_mlp.0", "tc_gemm_kernel rv-PE MLP layer 1", "tensor", 2.0 * B * N_img * 192 * 1024, tp)
+        kline("rv_pe_mlp.2", "tc_gemm_kernel rv-PE MLP layer 2", "tensor", 2.0 * B * N_img * 1024 * 256, tp)
+        del n_nodes
 
     if rank == 0:
         cpu = None
@@ -348,14 +465,18 @@ def main():
                                 parallelism=(f"K/V tokens split x{world}: queries replicated, one NCCL all-gather of "
                                              "(O, LSE) per decoder layer + LSE merge" if kv_split else
                                              f"frame sharding x{world}, no data-path collective"),
+                                feature_dtype=args.feat_dtype,
                                 l2="inputs (%.0f MB per step) exceed the 126 MB L2" % (h2d / 1e6),
                                 scope="forward_single from post-shared_conv BEV map + image features to task-head outputs",
-                                cuda_graph=not args.no_cuda_graph, eager_ms_per_step=ms_eager / args.steps),
+                                cuda_graph=not args.no_cuda_graph, eager_ms_per_step=ms_eager / args.steps,
+                                pinned_host_numa_cpus=(f"{numa.cpus[0]}-{numa.cpus[-1]} ({len(numa.cpus)})" if numa.cpus else None)),
                     clocks=clocks, gpu_launches=launches,
                     e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
-                    roofline=roof, cpu_baseline=cpu)
+                    parity=parity, roofline=roof, roofline_kernels=kernels, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print(f"bench.py: PARITY FAILED: frame 0 rel-L2 {parity['rel_l2']:.3e} > 1e-2", file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

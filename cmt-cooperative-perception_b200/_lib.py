@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmtcoop_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cmtcoop_b200.h")
 
-CMT_F32, CMT_BF16, CMT_BF16_SIMT = 0, 1, 3
+CMT_F32, CMT_BF16, CMT_F16, CMT_BF16_SIMT = 0, 1, 2, 3
 GEMM_RELU, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_TRANSPOSE_OUT = 1, 2, 4, 8
 
 _c = ctypes
@@ -28,7 +28,7 @@ SIGNATURES = {
     "cmt_ray_query_pe": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _i, _vp]),
     "cmt_masked_view_sum": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cmt_pos2embed": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "cmt_gather_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "cmt_gather_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cmt_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i,
                                _i64, _i64, _i64, _f, _i, _i, _i, _vp, _vp]),
     "cmt_cross_attn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -38,6 +38,7 @@ SIGNATURES = {
     "cmt_coop_max": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "cmt_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "cmt_task_head_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cmt_debug_attn_timing": (_i, [_vp]),
 }
 
 _lib = None

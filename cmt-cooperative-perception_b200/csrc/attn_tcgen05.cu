@@ -736,8 +736,8 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, bool static_shif
 // cycle count into the last 148 entries (gives the SM clock under load); with -DCMT_ATTN_TRACE
 // (`make EXTRA=-DCMT_ATTN_TRACE`) CTA 0 also fills the per-step clock64 stamps (tools/attn_trace.py).
 // nullptr switches it off.
-static long long* g_trace_buf = nullptr;
-int tc_attn_set_timing_buffer(long long* dev_buf) { g_trace_buf = dev_buf; return CMT_OK; }
+static long long* g_trace_buf[64] = {};   // per device; written only by the diagnostic entry below
+int tc_attn_set_timing_buffer(long long* dev_buf) { g_trace_buf[current_device()] = dev_buf; return CMT_OK; }
 
 size_t tc_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     if (B <= 0 || H <= 0 || Nq <= 0 || n_kv_tokens <= 0) return 0;
@@ -779,7 +779,7 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     p.part_o = reinterpret_cast<float*>(wsp);
     p.part_lse = p.part_o + slots * p.qblk * 32;
-    p.trace = g_trace_buf;
+    p.trace = g_trace_buf[current_device()];
     p.q_norm2 = (a.q_norm2 != nullptr && a.k_norm2 != nullptr) ? a.q_norm2 : nullptr;
     p.k_norm2 = a.k_norm2;
     p.kn_bstride = a.kn_bstride;
@@ -795,8 +795,9 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
     }
     p.unsafe_flags = reinterpret_cast<int*>(tail + static_cast<size_t>(a.B) * p.T * 8 + 8);
 
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    int attr_dev;
+    if (attr_once.need(&attr_dev)) {
         const void* fns[4] = {reinterpret_cast<const void*>(&tc_attn_db_kernel<false, false>),
                               reinterpret_cast<const void*>(&tc_attn_db_kernel<false, true>),
                               reinterpret_cast<const void*>(&tc_attn_db_kernel<true, false>),
@@ -805,7 +806,7 @@ int launch_tc_attn(const AttnArgs& a, void* workspace, size_t workspace_bytes, c
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, attndb::SMEM_BYTES);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attn_db)");
         }
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     CUtensorMap tq, tk, tv;
     {

@@ -30,9 +30,14 @@ struct DevInfo {
 static DevInfo g_dev[64];
 static std::once_flag g_dev_once[64];
 
-static const DevInfo& dev_info() {
+int current_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return dev;
+}
+
+static const DevInfo& dev_info() {
+    const int dev = current_device();
     std::call_once(g_dev_once[dev], [dev]() {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
@@ -173,12 +178,12 @@ int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int
     return launch_pos2embed(pos, out, N, pos_stride, F, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
-int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos, const float* rv_pos,
-                      void* xk, void* xv, int B, int C, int n_bev, int V, int n_img, int out_dtype,
-                      void* stream) {
+int cmt_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos, const float* rv_pos,
+                      void* xk, void* xv, int B, int C, int n_bev, int V, int n_img, int tok_begin, int tok_end,
+                      int feat_dtype, int out_dtype, void* stream) {
     CMT_REQUIRE_DEVICE();
-    return launch_gather_tokens(x_bev, x_img, bev_pos, rv_pos, xk, xv, B, C, n_bev, V, n_img, out_dtype,
-                                static_cast<cudaStream_t>(stream));
+    return launch_gather_tokens(x_bev, x_img, bev_pos, rv_pos, xk, xv, B, C, n_bev, V, n_img, tok_begin, tok_end,
+                                feat_dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
@@ -268,7 +273,6 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
     return launch_simt_attn(a, dtype == CMT_BF16_SIMT ? CMT_BF16 : dtype, s);
 }
 
-// debug hook (not part of the public header): per-phase clock64 accounting of tc_attn_kernel, CTA 0
 int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
                        int L, int M, int NH, int HC, int CMAX, float eps, void* stream) {
     CMT_REQUIRE_DEVICE();
@@ -276,7 +280,7 @@ int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, co
     return launch_task_head_tail(h, gamma, beta, w2, b2, out, L, M, NH, HC, CMAX, eps, static_cast<cudaStream_t>(stream));
 }
 
-int cmt_debug_attn_timing(void* dev_buf_32xi64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_32xi64)); }
+int cmt_debug_attn_timing(void* dev_buf_i64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_i64)); }
 
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B, int H,
                   int Nq, int o_dtype, void* stream) {

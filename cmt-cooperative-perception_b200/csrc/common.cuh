@@ -35,6 +35,21 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int device_sm_count();
 int require_sm100();
+int current_device();   // cudaGetDevice clamped to [0, 64)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting: remember, thread-safely,
+// which devices of this process already have it.  Usage:
+//     static DeviceOnce once;  int dev;
+//     if (once.need(&dev)) { ...cudaFuncSetAttribute...; once.mark(dev); }
+// Two threads racing on the same device both set the (idempotent) attribute; nothing else is shared.
+struct DeviceOnce {
+    unsigned long long done = 0;   // bit d = device d configured (accessed with atomics)
+    bool need(int* dev) {
+        *dev = current_device();
+        return ((__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> *dev) & 1ull) == 0;
+    }
+    void mark(int dev) { __atomic_fetch_or(&done, 1ull << dev, __ATOMIC_RELEASE); }
+};
 
 // Driver entry point for cuTensorMapEncodeTiled, fetched once through the runtime
 // (no link-time dependency on libcuda).

@@ -4,6 +4,8 @@
 // Reference arithmetic followed (never copied):
 //   gather : models/utils/cmt_transformer.py:105-110 + models/utils/petr_transformer.py:296-299
 //   coop   : models/dense_heads/cmt_head_coop.py:358,383-389
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace cmt {
@@ -14,21 +16,51 @@ constexpr int kTileTok = 32;
 // camera of frame b) x all C channels.  Phase 1 reads channel rows (128 contiguous bytes per
 // warp load) into a transposed smem tile [token][channel] (row pitch C+1 words -> conflict-free
 // writes); phase 2 lets each warp emit whole token rows (C contiguous elements) for xk and xv.
-template <bool kBf16>
+//
+// kIn: dtype of the feature maps -- CMT_F32, CMT_BF16 or CMT_F16.  The kernel rounds every feature to the
+// output dtype anyway, so a backbone / neck (or a host pipeline) that hands over 16-bit features halves the read
+// (and, end to end, the PCIe) traffic without changing the result of the bf16 path.  16-bit sources with an even
+// token count use 32-bit loads: each half-warp reads the 32 tokens of one channel (64 contiguous bytes), the two
+// halves take adjacent channels, which keeps the transposed shared-memory writes conflict-free.
+//
+// [tok_begin, tok_end): only these tokens of the concatenated BEV ++ image axis are produced (KV-token split across
+// GPUs: a rank gathers, projects and attends its own range only); row 0 of xk / xv is token tok_begin.
+template <int kIn>
+__device__ __forceinline__ float load_feat(const void* p, long long i) {
+    if (kIn == CMT_F32) return __ldg(reinterpret_cast<const float*>(p) + i);
+    const unsigned short raw = __ldg(reinterpret_cast<const unsigned short*>(p) + i);
+    if (kIn == CMT_BF16) return __uint_as_float(static_cast<uint32_t>(raw) << 16);
+    return __half2float(__ushort_as_half(raw));
+}
+template <int kIn>
+__device__ __forceinline__ void unpack_feat2(uint32_t w, float& lo, float& hi) {
+    if (kIn == CMT_BF16) {
+        lo = __uint_as_float(w << 16);
+        hi = __uint_as_float(w & 0xffff0000u);
+    } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        lo = f.x;
+        hi = f.y;
+    }
+}
+
+template <bool kBf16, int kIn>
 __global__ void __launch_bounds__(256) gather_tokens_kernel(
-    const float* __restrict__ x_bev, const float* __restrict__ x_img,
+    const void* __restrict__ x_bev, const void* __restrict__ x_img,
     const float* __restrict__ bev_pos, const float* __restrict__ rv_pos, void* __restrict__ xk,
-    void* __restrict__ xv, int C, int n_bev, int V, int n_img, int tiles_bev, int tiles_img) {
+    void* __restrict__ xv, int C, int n_bev, int V, int n_img, int tiles_bev, int tiles_img, int tok_begin,
+    int tok_end) {
     extern __shared__ float tile[];  // [kTileTok][C + 1]
+    constexpr int ESZ = kIn == CMT_F32 ? 4 : 2;
     const int b = blockIdx.y;
     const int pitch = C + 1;
     int tix = blockIdx.x;
-    const float* src;       // [C, n_src] channel-major
-    const float* pos;       // [n_src, C] token-major (already offset to this source's first token)
+    const unsigned char* src;   // [C, n_src] channel-major
+    const float* pos;           // [n_src, C] token-major (already offset to this source's first token)
     int n_src, t0;
-    long long dst_tok0;     // first destination token of this source inside the frame
+    long long dst_tok0;         // first destination token of this source inside the frame
     if (tix < tiles_bev) {
-        src = x_bev + static_cast<long long>(b) * C * n_bev;
+        src = reinterpret_cast<const unsigned char*>(x_bev) + static_cast<long long>(b) * C * n_bev * ESZ;
         pos = bev_pos;
         n_src = n_bev;
         t0 = tix * kTileTok;
@@ -37,25 +69,40 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(
         tix -= tiles_bev;
         const int v = tix / tiles_img;
         const int cam = b * V + v;
-        src = x_img + static_cast<long long>(cam) * C * n_img;
+        src = reinterpret_cast<const unsigned char*>(x_img) + static_cast<long long>(cam) * C * n_img * ESZ;
         pos = rv_pos + static_cast<long long>(cam) * n_img * C;
         n_src = n_img;
         t0 = (tix % tiles_img) * kTileTok;
         dst_tok0 = n_bev + static_cast<long long>(v) * n_img;
     }
+    // tiles entirely outside this rank's token range have nothing to do (block-uniform)
+    if (dst_tok0 + t0 >= tok_end || dst_tok0 + t0 + kTileTok <= tok_begin) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tok = t0 + lane;
-    const bool tok_ok = tok < n_src;
-    for (int c = warp; c < C; c += 8) {
-        const float val = tok_ok ? __ldg(src + static_cast<long long>(c) * n_src + tok) : 0.0f;
-        tile[lane * pitch + c] = val;
+    if (kIn != CMT_F32 && (n_src & 1) == 0) {
+        // 16-bit features, even token count: lanes 0-15 read channel c, lanes 16-31 channel c + 1, two tokens per lane
+        const int half = lane >> 4, l16 = lane & 15;
+        const int tok = t0 + 2 * l16;
+        for (int c = 2 * warp + half; c < C; c += 16) {
+            float lo = 0.0f, hi = 0.0f;
+            if (tok < n_src)   // n_src even and tok even: both tokens are in range
+                unpack_feat2<kIn>(__ldg(reinterpret_cast<const uint32_t*>(src + (static_cast<long long>(c) * n_src + tok) * 2)), lo, hi);
+            tile[(2 * l16) * pitch + c] = lo;
+            tile[(2 * l16 + 1) * pitch + c] = hi;
+        }
+    } else {
+        const int tok = t0 + lane;
+        const bool tok_ok = tok < n_src;
+        for (int c = warp; c < C; c += 8)
+            tile[lane * pitch + c] = tok_ok ? load_feat<kIn>(src, static_cast<long long>(c) * n_src + tok) : 0.0f;
     }
     __syncthreads();
-    const long long N_kv = n_bev + static_cast<long long>(V) * n_img;
+    const long long n_out = tok_end - tok_begin;
     for (int r = warp; r < kTileTok; r += 8) {
         const int st = t0 + r;
         if (st >= n_src) break;
-        const long long drow = (static_cast<long long>(b) * N_kv + dst_tok0 + st) * C;
+        const long long gtok = dst_tok0 + st;
+        if (gtok < tok_begin || gtok >= tok_end) continue;
+        const long long drow = (static_cast<long long>(b) * n_out + (gtok - tok_begin)) * C;
         const float* prow = pos + static_cast<long long>(st) * C;
         const float* trow = tile + r * pitch;
         for (int c = lane * 2; c < C; c += 64) {
@@ -74,29 +121,37 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(
     }
 }
 
-int launch_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                          const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                         int n_img, int out_dtype, cudaStream_t stream) {
+                         int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, cudaStream_t stream) {
     CMT_CHECK_ARG(xk && xv, "cmt_gather_tokens: null output");
     CMT_CHECK_ARG(B > 0 && C > 0 && (C % 2) == 0, "cmt_gather_tokens: bad B/C");
     CMT_CHECK_ARG(n_bev >= 0 && V >= 0 && n_img >= 0, "cmt_gather_tokens: bad token counts");
     CMT_CHECK_ARG(n_bev == 0 || (x_bev && bev_pos), "cmt_gather_tokens: BEV pointers missing");
     CMT_CHECK_ARG(V == 0 || n_img == 0 || (x_img && rv_pos), "cmt_gather_tokens: image pointers missing");
-    CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gather_tokens: bad dtype");
+    CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gather_tokens: bad output dtype");
+    CMT_CHECK_ARG(feat_dtype == CMT_F32 || feat_dtype == CMT_BF16 || feat_dtype == CMT_F16, "cmt_gather_tokens: bad feature dtype");
     CMT_CHECK_ARG(B <= 65535, "cmt_gather_tokens: batch too large for one launch");
+    const long long n_kv = n_bev + static_cast<long long>(V) * n_img;
+    CMT_CHECK_ARG(0 <= tok_begin && tok_begin <= tok_end && tok_end <= n_kv, "cmt_gather_tokens: bad token range [%d,%d) of %lld",
+                  tok_begin, tok_end, n_kv);
+    CMT_CHECK_ARG(feat_dtype == CMT_F32 || ((reinterpret_cast<uintptr_t>(x_bev) | reinterpret_cast<uintptr_t>(x_img)) & 3) == 0,
+                  "cmt_gather_tokens: 16-bit feature maps must be 4-byte aligned");
     const int tiles_bev = (n_bev + kTileTok - 1) / kTileTok;
     const int tiles_img = (n_img + kTileTok - 1) / kTileTok;
     const int tiles = tiles_bev + V * tiles_img;
-    if (tiles == 0) return CMT_OK;
+    if (tiles == 0 || tok_begin == tok_end) return CMT_OK;
     const size_t smem = static_cast<size_t>(kTileTok) * (C + 1) * sizeof(float);
     CMT_CHECK_ARG(smem <= 48 * 1024, "cmt_gather_tokens: C too large (%d)", C);
     dim3 grid(tiles, B);
-    if (out_dtype == CMT_BF16)
-        gather_tokens_kernel<true><<<grid, 256, smem, stream>>>(
-            x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, n_img, tiles_bev, tiles_img);
-    else
-        gather_tokens_kernel<false><<<grid, 256, smem, stream>>>(
-            x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, n_img, tiles_bev, tiles_img);
+#define CMT_GATHER_LAUNCH(OUT_BF16, IN)                                                                       \
+    gather_tokens_kernel<OUT_BF16, IN><<<grid, 256, smem, stream>>>(x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, \
+                                                                    n_img, tiles_bev, tiles_img, tok_begin, tok_end)
+    const bool ob = out_dtype == CMT_BF16;
+    if (feat_dtype == CMT_F32) { if (ob) CMT_GATHER_LAUNCH(true, CMT_F32); else CMT_GATHER_LAUNCH(false, CMT_F32); }
+    else if (feat_dtype == CMT_BF16) { if (ob) CMT_GATHER_LAUNCH(true, CMT_BF16); else CMT_GATHER_LAUNCH(false, CMT_BF16); }
+    else { if (ob) CMT_GATHER_LAUNCH(true, CMT_F16); else CMT_GATHER_LAUNCH(false, CMT_F16); }
+#undef CMT_GATHER_LAUNCH
     CMT_LAUNCH_CHECK("cmt_gather_tokens");
     return CMT_OK;
 }

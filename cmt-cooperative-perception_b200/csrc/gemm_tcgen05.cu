@@ -143,9 +143,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     const bool bias_cached = p.bias != nullptr && !p.bias_per_row && p.N <= BIAS_CAP - 64;
+    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor
+    // the bias may have been produced on the stream by a predecessor (C-ABI callers, rebuilt weight caches): read it
+    // only after the dependency wait (plain loads: __ldg's non-coherent path could serve a stale line)
     if (bias_cached)
-        for (int i = threadIdx.x; i < BIAS_CAP; i += THREADS) bias_s[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
-    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch, bias cache: weights) overlapped the predecessor
+        for (int i = threadIdx.x; i < BIAS_CAP; i += THREADS) bias_s[i] = i < p.N ? p.bias[i] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -495,12 +497,13 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
                   "cmt_gemm_bias_act(bf16): column block must be >= N or a multiple of 32");
     CMT_CHECK_ARG(g.strideA % 8 == 0 && g.strideB % 8 == 0, "cmt_gemm_bias_act(bf16): batch strides must be multiples of 8");
 
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    int attr_dev;
+    if (attr_once.need(&attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm)");
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
 
     CUtensorMap ta, tb;

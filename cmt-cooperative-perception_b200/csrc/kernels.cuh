@@ -44,9 +44,9 @@ int launch_masked_view_sum(const void* emb, const float* mask, float* out, int B
 int launch_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype,
                      cudaStream_t stream);
 // gather_kernels.cu
-int launch_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                          const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                         int n_img, int out_dtype, cudaStream_t stream);
+                         int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, cudaStream_t stream);
 int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
                      int B, int H, int Nq, int o_dtype, cudaStream_t stream);

@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (CMT_BF16, CMT_BF16_SIMT, CMT_F32, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_RELU,
+from ._lib import (CMT_BF16, CMT_BF16_SIMT, CMT_F16, CMT_F32, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_RELU,
                    GEMM_TRANSPOSE_OUT)
 
 HEAD_DIM = 32
@@ -41,6 +41,32 @@ def profile_events(name: str, enable: bool):
     pairs = _profile.pop(name, [])
     torch.cuda.synchronize()
     return [a.elapsed_time(b) for a, b in pairs]
+
+
+class _timed:
+    """Records a CUDA-event pair around the launches of one op on the launching stream when bench.py asked for
+    that tag (profile_events); otherwise free."""
+
+    def __init__(self, tag, ref):
+        self.ev = _profile.get(tag) if tag is not None and _profile else None
+        self.ref = ref
+
+    def __enter__(self):
+        if self.ev is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.ref.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.e1.record(torch.cuda.current_stream(self.ref.device))
+            self.ev.append((self.e0, self.e1))
+        return False
+
+
+# bench.py switch: ignore the operand-norm maxima so that every attention item takes the online-softmax kernel
+# (what a checkpoint with peaky logits, score bound > 60, would run); never set by the library itself
+FORCE_ONLINE_SOFTMAX = False
 
 
 def _dt(dtype) -> int:
@@ -80,7 +106,7 @@ def ray_pe(img2lidar, H, W, depth_num, pad_h, pad_w, pc_range, out_dtype=torch.b
     n_cam = m.shape[0]
     out = torch.empty((n_cam, H, W, depth_num * 3), dtype=out_dtype, device=m.device)
     lib = _lib.load()
-    with torch.cuda.device(m.device):
+    with torch.cuda.device(m.device), _timed("ray_pe", m):
         rc = lib.cmt_ray_pe(_ptr(m), _ptr(out), n_cam, H, W, depth_num, float(pad_h), float(pad_w),
                             ctypes.cast(_pc(pc_range), ctypes.c_void_p), _dt(out_dtype), _stream(m))
     _lib.check(rc, "cmt_ray_pe")
@@ -136,34 +162,42 @@ def pos2embed(pos, num_pos_feats=128, out_dtype=torch.bfloat16):
     return out
 
 
-def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16):
+_FEAT_DTYPES = {torch.float32: CMT_F32, torch.bfloat16: CMT_BF16, torch.float16: CMT_F16}
+
+
+def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16, tok_range=None):
     """K4 (cmt_transformer.py:105-110 + petr_transformer.py:296-299).
-    x_bev [B,C,Hb,Wb] | None, x_img [B*V,C,h,w] | None, bev_pos [N_bev,C], rv_pos [B*V*h*w, C] (any
-    leading shape) -> xk = mem+pos, xv = mem, both [B,N_kv,C]."""
+    x_bev [B,C,Hb,Wb] | None, x_img [B*V,C,h,w] | None (fp32, bf16 or fp16 -- both the same dtype),
+    bev_pos [N_bev,C], rv_pos [B*V*h*w, C] (any leading shape) fp32 -> xk = mem+pos, xv = mem, both
+    [B,N_kv,C]; with tok_range=(lo, hi) only those tokens of the concatenated axis: [B,hi-lo,C]."""
     ref = x_bev if x_bev is not None else x_img
     dev = ref.device
     C = ref.shape[1]
+    fdt = ref.dtype
+    if fdt not in _FEAT_DTYPES:
+        raise TypeError(f"feature maps must be fp32, bf16 or fp16, got {fdt}")
     n_bev = 0
     n_img = 0
     if x_bev is not None:
-        x_bev = _cuda(x_bev, "x_bev", torch.float32)
+        x_bev = _cuda(x_bev, "x_bev", fdt)
         bev_pos = _cuda(bev_pos, "bev_pos", torch.float32)
         n_bev = x_bev.shape[2] * x_bev.shape[3]
         assert x_bev.shape[0] == B and bev_pos.numel() == n_bev * C
     if x_img is not None:
-        x_img = _cuda(x_img, "x_img", torch.float32)
+        x_img = _cuda(x_img, "x_img", fdt)
         rv_pos = _cuda(rv_pos, "rv_pos", torch.float32)
         n_img = x_img.shape[2] * x_img.shape[3]
         assert x_img.shape[0] == B * V and rv_pos.numel() == B * V * n_img * C
     else:
         V = 0
     N_kv = n_bev + V * n_img
-    xk = torch.empty((B, N_kv, C), dtype=out_dtype, device=dev)
-    xv = torch.empty((B, N_kv, C), dtype=out_dtype, device=dev)
+    lo, hi = (0, N_kv) if tok_range is None else tok_range
+    xk = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
+    xv = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
     lib = _lib.load()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("gather_tokens", ref):
         rc = lib.cmt_gather_tokens(_ptr(x_bev), _ptr(x_img), _ptr(bev_pos), _ptr(rv_pos), _ptr(xk), _ptr(xv),
-                                   B, C, n_bev, V, n_img, _dt(out_dtype), _stream(ref))
+                                   B, C, n_bev, V, n_img, lo, hi, _FEAT_DTYPES[fdt], _dt(out_dtype), _stream(ref))
     _lib.check(rc, "cmt_gather_tokens")
     _count()
     return xk, xv
@@ -171,7 +205,7 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16)
 
 def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=1, strideA=0, strideB=0,
          strideC=0, alpha=1.0, relu=False, bias_per_row=False, force_simt=False, transpose_out=False,
-         norm2_max=None):
+         norm2_max=None, tag=None):
     """Raw cmt_gemm_bias_act: C = act((A B^T + bias) * alpha) with column-block output addressing.
     norm2_max: optional zero-initialised fp32 [batch, N/32] receiving max |row block|^2 (bf16 path)."""
     A = _cuda(A, "A")
@@ -182,7 +216,7 @@ def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=
     flags = ((GEMM_RELU if relu else 0) | (GEMM_BIAS_PER_ROW if bias_per_row else 0) |
              (GEMM_FORCE_SIMT if force_simt else 0) | (GEMM_TRANSPOSE_OUT if transpose_out else 0))
     lib = _lib.load()
-    with torch.cuda.device(A.device):
+    with torch.cuda.device(A.device), _timed(tag, A):
         rc = lib.cmt_gemm_bias_act(_ptr(A), _ptr(Bm), _ptr(bias), _ptr(C), M, N, K, lda, ldb, ldc,
                                    cb if cb is not None else max(N, 1), cb_stride, batch, strideA, strideB, strideC,
                                    float(alpha), flags, _dt(A.dtype), _dt(C.dtype), _ptr(norm2_max), _stream(A))
@@ -191,7 +225,7 @@ def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=
     return C
 
 
-def linear(x, weight, bias=None, *, relu=False, alpha=1.0, out_dtype=None, force_simt=False):
+def linear(x, weight, bias=None, *, relu=False, alpha=1.0, out_dtype=None, force_simt=False, tag=None):
     """act((x @ weight.T + bias) * alpha) -- F.linear replacement. x [..., K], weight [N, K]."""
     K = x.shape[-1]
     N = weight.shape[0]
@@ -201,7 +235,7 @@ def linear(x, weight, bias=None, *, relu=False, alpha=1.0, out_dtype=None, force
     M = x2.shape[0]
     out_dtype = out_dtype or x.dtype
     out = torch.empty((M, N), dtype=out_dtype, device=x.device)
-    gemm(x2, weight, bias, out, M, N, K, lda=K, ldb=K, ldc=N, alpha=alpha, relu=relu, force_simt=force_simt)
+    gemm(x2, weight, bias, out, M, N, K, lda=K, ldb=K, ldc=N, alpha=alpha, relu=relu, force_simt=force_simt, tag=tag)
     return out.reshape(*x.shape[:-1], N)
 
 
@@ -228,7 +262,8 @@ def project_keys(xk, w, bias, n_layers, H, out=None, norm2_max=None):
     if out is None:
         out = torch.empty((B, n_layers, H, N_kv, HEAD_DIM), dtype=xk.dtype, device=xk.device)
     gemm(xk, w, bias, out, N_kv, NO, C, lda=C, ldb=C, ldc=HEAD_DIM, cb=HEAD_DIM, cb_stride=N_kv * HEAD_DIM,
-         batch=B, strideA=N_kv * C, strideB=0, strideC=n_layers * H * N_kv * HEAD_DIM, norm2_max=norm2_max)
+         batch=B, strideA=N_kv * C, strideB=0, strideC=n_layers * H * N_kv * HEAD_DIM, norm2_max=norm2_max,
+         tag="k_proj" if n_layers > 1 else None)
     return out
 
 
@@ -245,7 +280,7 @@ def project_values_t(xv, w, bias, n_layers, H, out=None):
         # tokens on the M side like the K projection (the CTA keeps its slice of W_v resident in shared memory and
         # streams token tiles), each [tokens, 32] head block stored transposed
         gemm(xv, w, bias, out, N_kv, NO, C, lda=C, ldb=C, ldc=ld, cb=HEAD_DIM, cb_stride=HEAD_DIM * ld, batch=B,
-             strideA=N_kv * C, strideB=0, strideC=NO * ld, transpose_out=True)
+             strideA=N_kv * C, strideB=0, strideC=NO * ld, transpose_out=True, tag="v_proj" if n_layers > 1 else None)
     else:
         gemm(w, xv, bias, out, NO, N_kv, C, lda=C, ldb=C, ldc=ld, batch=B, strideA=0, strideB=N_kv * C,
              strideC=NO * ld, bias_per_row=True)
@@ -301,7 +336,7 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         key_keep = key_keep.to(torch.uint8).contiguous()
     qn = kn = None
     kn_stride = 0
-    if q_norm2 is not None and k_norm2 is not None and dt == CMT_BF16:
+    if q_norm2 is not None and k_norm2 is not None and dt == CMT_BF16 and not FORCE_ONLINE_SOFTMAX:
         qn = _cuda(q_norm2, "q_norm2", torch.float32)
         k_norm2 = _cuda(k_norm2, "k_norm2", torch.float32)
         assert qn.shape == (B, H) and k_norm2.shape == (B, L, H)

@@ -70,7 +70,7 @@ class FlashAttention(nn.Module):
         k = kv[:, :, 0].permute(0, 2, 1, 3).to(dt).contiguous().view(B, 1, H, S, D)
         ld = (S + 7) // 8 * 8
         vt = torch.zeros((B, 1, H, D, ld), dtype=dt, device=q.device)
-        vt[..., :S] = kv[:, :, 1].permute(0, 2, 3, 1).to(dt)
+        vt[:, 0, :, :, :S] = kv[:, :, 1].permute(0, 2, 3, 1).to(dt)   # [B,H,D,S] into the single-layer cache
         o = ops.cross_attn(qs, k, vt, 0, o_dtype=torch.float32,
                            key_keep=None if key_padding_mask is None else key_padding_mask.to(q.device).bool())
         return o.view(B, T, H, D), None
@@ -82,6 +82,10 @@ class FlashMHA(nn.Module):
     def __init__(self, embed_dim, num_heads, bias=True, batch_first=True, attention_dropout=0.0,
                  causal=False, device=None, dtype=None, **kwargs):
         assert batch_first
+        if causal:
+            # the reference forwards causal=self.causal to the inner attention (attention.py:136); no CMT config sets it
+            # and the tcgen05 kernel has no causal mask: refuse instead of silently computing non-causal attention
+            raise NotImplementedError("FlashMHA(causal=True): causal attention is not on the CMT path (attention.py:98)")
         super().__init__()
         self.embed_dim = embed_dim
         self.causal = causal

@@ -2,11 +2,14 @@
 constructor arguments, forward signatures and state-dict keys
 (projects/mmdet3d_plugin/models/dense_heads/cmt_head.py:97-1085), inference path only.
 
-What runs where:
+What runs where (default bf16 inference path):
   * camera-ray PE lift, re-projection of the reference points, sine/cosine embedding, masked view
-    sum, token gather, every PE-MLP / projection GEMM and the cross-attention: libcmtcoop_b200.
-  * shared_conv (cuDNN), self-attention / LayerNorm / FFN over the 900 queries, the grouped Conv1d
-    task heads: torch CUDA ops ("next" rows).
+    sum, token gather, every PE-MLP / projection GEMM, the cross-attention AND the decoder's small ops
+    (900x900 self-attention, LayerNorms, FFN: plugin/fused_decoder.py) run in libcmtcoop_b200 -- bf16
+    operands on the tensor cores, fp32 accumulation / residuals / statistics.  The reference computes the
+    decoder in fp32 (nn.MultiheadAttention, nn.Linear); the difference is inside the 1e-2 rel-L2 budget of
+    the bf16 mode and `set_precision('fp32')` selects the fp32 CUDA-core kernels (<= 1e-4).
+  * the task heads always compute in fp32 (their logits feed the top-k).
 Losses, denoising queries and target assignment are training-only and not part of this package.
 """
 from __future__ import annotations
@@ -289,12 +292,12 @@ class _CmtHeadBase(nn.Module):
             self._cache["w_" + name] = hit
         return hit[1]
 
-    def _mlp(self, name, x):
+    def _mlp(self, name, x, tag=None):
         """Linear -> ReLU -> Linear (cmt_head.py:292-301); hidden activation in the compute dtype, fp32 out."""
         w0, b0, w1, b1 = self._mlp_weights(name)
         dt = _compute_dtype(self.precision)
-        h = ops.linear(x.to(dt), w0, b0, relu=True, out_dtype=dt)
-        return ops.linear(h, w1, b1, out_dtype=torch.float32)
+        h = ops.linear(x.to(dt), w0, b0, relu=True, out_dtype=dt, tag=None if tag is None else tag + ".0")
+        return ops.linear(h, w1, b1, out_dtype=torch.float32, tag=None if tag is None else tag + ".2")
 
     # -- position encodings -----------------------------------------------------------------
     def _matrices(self, img_metas, device):
@@ -322,7 +325,7 @@ class _CmtHeadBase(nn.Module):
             mats = self._matrices(img_metas, img_feats.device)
         dt = _compute_dtype(self.precision)
         coords = ops.ray_pe(mats[1].reshape(-1, 4, 4), H, W, self.depth_num, pad_h, pad_w, self.pc_range, out_dtype=dt)
-        return self._mlp("rv_embedding", coords)
+        return self._mlp("rv_embedding", coords, tag="rv_pe_mlp")
 
     def _bev_pos_embed(self, device):
         """bev_embedding(pos2embed(coords_bev)) (cmt_head.py:489): input independent -> cached per weights."""

@@ -79,29 +79,35 @@ class _CmtTransformerBase(nn.Module):
             self._kv_w = (key, (wk, bk, wv, bv))
         return self._kv_w[1]
 
+    def kv_token_range(self, n_kv):
+        """Token range [lo, hi) of the concatenated BEV ++ image axis this rank gathers, projects and attends:
+        everything unless the KV-token split is enabled (then a tile-aligned share, parallel.kv_split_range)."""
+        if self.kv_split_group is None:
+            return 0, n_kv
+        import torch.distributed as dist
+        from .. import parallel
+        return parallel.kv_split_range(n_kv, dist.get_rank(self.kv_split_group), dist.get_world_size(self.kv_split_group))
+
     def build_kv_cache(self, x_bev, x_img, bev_pos, rv_pos, B, V):
-        """gather (K4) + all-layer K / V^T projection (K2).  Returns (KVCache, xv [B,N_kv,C])."""
+        """gather (K4) + all-layer K / V^T projection (K2).  Returns (KVCache, xv [B,n_tok,C]) where n_tok is
+        this rank's share of the token axis (all tokens without the KV-token split)."""
         dt = _compute_dtype(self.precision)
-        xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt)
-        wk, bk, wv, bv = self._stacked_kv_weights()
+        n_kv = (x_bev.shape[2] * x_bev.shape[3] if x_bev is not None else 0) + \
+               (V * x_img.shape[2] * x_img.shape[3] if x_img is not None else 0)
+        lo, hi = self.kv_token_range(n_kv)
+        group = self.kv_split_group
         L = len(self.decoder.layers)
         H = self.decoder.layers[0].attentions[-1].num_heads
-        group = self.kv_split_group
-        if group is not None:
-            # KV-token split: this rank projects and attends only its tile-aligned token range
-            import torch.distributed as dist
-            from .. import parallel
-            lo, hi = parallel.kv_split_range(xk.shape[1], dist.get_rank(group), dist.get_world_size(group))
-            if hi <= lo:
-                return KVCache(None, None, 0, group), xv
-            xk_l, xv_l = xk[:, lo:hi].contiguous(), xv[:, lo:hi].contiguous()
-            kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
-            return KVCache(ops.project_keys(xk_l, wk, bk, L, H, norm2_max=kn2), ops.project_values_t(xv_l, wv, bv, L, H),
-                           hi - lo, group, k_norm2=kn2), xv
+        if hi <= lo:   # more ranks than token tiles: this rank contributes the neutral element of the merge
+            return KVCache(None, None, 0, group), None
+        # with the split, the gather kernel itself produces only the rank's rows: K1/K4/K2 all shard with the tokens
+        xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt,
+                                   tok_range=None if group is None else (lo, hi))
+        wk, bk, wv, bv = self._stacked_kv_weights()
         kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
         k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)
         vt = ops.project_values_t(xv, wv, bv, L, H)
-        return KVCache(k, vt, xk.shape[1], k_norm2=kn2), xv
+        return KVCache(k, vt, hi - lo, group, k_norm2=kn2), xv
 
     def enable_kv_split(self, group=None):
         """Split the K/V token axis across the ranks of `group` (default: the WORLD group); every rank
@@ -135,7 +141,7 @@ class CmtTransformer(_CmtTransformerBase):
         cache, xv = self.build_kv_cache(x.contiguous(), x_img.contiguous(), bev_pos_embed.contiguous(),
                                         rv_pos_embed.contiguous(), bs, V)
         out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
-        return out_dec, xv.transpose(0, 1)  # memory as [N_kv,B,C] (compute dtype)
+        return out_dec, (None if xv is None else xv.transpose(0, 1))  # memory as [N_kv,B,C] (compute dtype)
 
 
 @TRANSFORMER.register_module()
@@ -147,7 +153,7 @@ class CmtLidarTransformer(_CmtTransformerBase):
         bs = x.shape[0]
         cache, xv = self.build_kv_cache(x.contiguous(), None, pos_embed.contiguous(), None, bs, 0)
         out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
-        return out_dec, xv.transpose(0, 1)
+        return out_dec, (None if xv is None else xv.transpose(0, 1))
 
 
 @TRANSFORMER.register_module()
@@ -158,4 +164,4 @@ class CmtImageTransformer(_CmtTransformerBase):
         V = x_img.shape[0] // bs
         cache, xv = self.build_kv_cache(None, x_img.contiguous(), None, rv_pos_embed.contiguous(), bs, V)
         out_dec = self._decode(cache, query_embed, attn_masks, reg_branch)
-        return out_dec, xv.transpose(0, 1)
+        return out_dec, (None if xv is None else xv.transpose(0, 1))

@@ -25,6 +25,10 @@ from .attention import KVCache, _Q_SCALE, _compute_dtype
 
 _STD_ORDER = ("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")
 
+# diagnostics for bench.py: the operand-norm maxima of the last forward, (q_norm2 [L,B,H], k_norm2 [B,L,H]) or None.
+# An attention item (layer, frame, head) takes the static-shift kernel iff sqrt(qn * kn) * 1.0079 + 1e-3 <= 60.
+last_norms = None
+
 
 def _cached(module, tag, key, build):
     store = module.__dict__.setdefault("_cmt_cache", {})
@@ -106,6 +110,8 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
     static_shift = cache.k_norm2 is not None and dt == torch.bfloat16
     qn2 = torch.zeros((L, B, H), dtype=torch.float32, device=dev) if static_shift else None
 
+    global last_norms
+    last_norms = (qn2, cache.k_norm2) if static_shift else None
     for li, layer in enumerate(decoder.layers):
         # ---- self-attention over the queries: q = k = x + query_pos, v = x (key_pos = query_pos) ----
         sw = _mha_weights(layer.attentions[0].attn, dt)

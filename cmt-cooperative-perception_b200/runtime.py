@@ -15,21 +15,68 @@ graph for a fixed batch shape and calibration and replays it: no per-launch host
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
+class numa_local_to_gpu:
+    """Context manager: while active, the calling thread runs on the CPU cores NVML reports as local to GPU
+    `device_index`, so pinned host buffers allocated (first touched) inside land on that GPU's NUMA node -- with 4 or 8
+    ranks streaming features at PCIe rate, remote-node staging buffers are what a dual-socket host runs out of first.
+    Restores the previous affinity on exit; a no-op when NVML or sched_setaffinity are unavailable."""
+
+    def __init__(self, device_index: int):
+        self.index = device_index
+        self.prev = None
+        self.cpus = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            n_words = (os.cpu_count() + 63) // 64
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                self.prev = allowed
+                os.sched_setaffinity(0, cpus)
+                self.cpus = sorted(cpus)
+        except Exception:
+            self.prev = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+        return False
+
+
 class PipelinedRunner:
-    def __init__(self, head, img_metas, example_inputs: dict, device, use_cuda_graph: bool = False):
+    def __init__(self, head, img_metas, example_inputs: dict, device, use_cuda_graph: bool = False,
+                 keep_results: bool = True):
         """example_inputs: {name: pinned CPU tensor} with the feature tensors `forward_single` takes
-        (pts_feats / img_feats, or the four vehicle_/infrastructure_ entries for the coop heads).
-        use_cuda_graph: replay one captured forward per device input slot instead of launching eagerly."""
+        (pts_feats / img_feats, or the four vehicle_/infrastructure_ entries for the coop heads); fp32, bf16 or
+        fp16 -- the gather kernel rounds every feature to the compute dtype on arrival, so 16-bit features halve
+        the PCIe traffic without changing a single output bit in bf16 mode.
+        use_cuda_graph: replay one captured forward per device input slot instead of launching eagerly.
+        keep_results: `run` returns every batch's outputs as ordinary CPU tensors (copied out of the two pinned
+        staging buffers before those are reused); False keeps only the staging buffers (results of the last two
+        batches), for callers that consume results through `on_result`."""
         self.head = head
         self.metas = img_metas
         self.dev = torch.device(device)
         self.coop = type(head).__name__.endswith("Coop")
-        self.keys = list(example_inputs.keys())
-        self.dbuf = [{k: torch.empty_like(v, device=self.dev) for k, v in example_inputs.items()} for _ in range(2)]
-        self.hout = [None, None]
+        self.keys = [k for k, v in example_inputs.items() if v is not None]
+        self.dbuf = [{k: torch.empty_like(example_inputs[k], device=self.dev) for k in self.keys} for _ in range(2)]
+        self.hout = [None, None]                                   # per slot: list (tasks) of {name: pinned tensor}
+        self.keep_results = keep_results
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
         self.ev_in = [torch.cuda.Event() for _ in range(2)]       # copy-in of slot done
@@ -37,7 +84,7 @@ class PipelinedRunner:
         self.ev_done = [torch.cuda.Event() for _ in range(2)]     # compute of slot done
         self.ev_out = [torch.cuda.Event() for _ in range(2)]      # copy-out of slot done
         self._primed = [False, False]
-        self.h2d_bytes = int(sum(v.numel() * v.element_size() for v in example_inputs.values()))
+        self.h2d_bytes = int(sum(example_inputs[k].numel() * example_inputs[k].element_size() for k in self.keys))
         self.d2h_bytes = 0
         self.graphs = None
         if use_cuda_graph:
@@ -55,49 +102,75 @@ class PipelinedRunner:
         return self.head.forward_single(g("pts_feats"), g("img_feats"), self.metas)
 
     def _enqueue_copy_in(self, slot, host_inputs):
-        cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             if self._primed[slot]:
                 self.s_in.wait_event(self.ev_free[slot])   # the previous user of this slot has consumed it
             for k in self.keys:
                 self.dbuf[slot][k].copy_(host_inputs[k], non_blocking=True)
             self.ev_in[slot].record(self.s_in)
-        del cur
+
+    def _collect(self, slot):
+        """Host copy of the staging buffers of `slot` once its device->host transfer has landed."""
+        self.ev_out[slot].synchronize()
+        return [{n: t.clone() for n, t in task.items()} for task in self.hout[slot]]
 
     @torch.no_grad()
-    def run(self, host_batches):
-        """host_batches: iterable of {name: pinned CPU tensor}.  Returns the list of per-batch results
-        (dicts of pinned CPU tensors, valid after the final synchronize this method performs)."""
+    def run(self, host_batches, on_result=None):
+        """host_batches: iterable of {name: pinned CPU tensor}.  Returns one entry per batch: the list (one dict per
+        task) of head outputs as CPU tensors.  Every device->host copy has completed when this returns.
+        on_result(i, staging): optional callback invoked with the pinned staging dicts of batch i right after its
+        transfer completed (zero-copy consumers); with keep_results=False the returned list holds None for every
+        batch but the last two, whose entries are the staging buffers themselves."""
         cur = torch.cuda.current_stream(self.dev)
         batches = list(host_batches)
-        results = []
+        results = [None] * len(batches)
         if not batches:
             return results
+        pending = [None, None]                                      # batch index whose outputs sit in the slot
         self._enqueue_copy_in(0, batches[0])
         for i, _ in enumerate(batches):
             slot = i & 1
             if i + 1 < len(batches):
                 self._enqueue_copy_in(slot ^ 1, batches[i + 1])     # overlaps this step's compute
             cur.wait_event(self.ev_in[slot])
-            if self.hout[slot] is not None:
-                cur.wait_event(self.ev_out[slot])                   # result buffers of this slot are free again
+            if pending[slot] is not None:
+                # the staging buffers of this slot still hold batch i-2: hand it out before they are overwritten
+                j = pending[slot]
+                if on_result is not None:
+                    self.ev_out[slot].synchronize()
+                    on_result(j, self.hout[slot])
+                if self.keep_results:
+                    results[j] = self._collect(slot)
+                pending[slot] = None
+            if self._primed[slot]:
+                # a graph's static outputs are overwritten by the slot's next replay, and the staging buffers by the
+                # next copy-out: both wait for the copy-out of the slot's previous batch
+                cur.wait_event(self.ev_out[slot])
             rets = self.graphs[slot]() if self.graphs is not None else self._forward(self.dbuf[slot])
             self.ev_free[slot].record(cur)
             self._primed[slot] = True
-            outs = rets[0]
             if self.hout[slot] is None:
-                self.hout[slot] = {n: torch.empty(t.shape, dtype=t.dtype).pin_memory() for n, t in outs.items()}
-                self.d2h_bytes = int(sum(t.numel() * t.element_size() for t in outs.values()))
+                self.hout[slot] = [{n: torch.empty(t.shape, dtype=t.dtype).pin_memory() for n, t in task.items()}
+                                   for task in rets]
+                self.d2h_bytes = int(sum(t.numel() * t.element_size() for task in rets for t in task.values()))
             self.ev_done[slot].record(cur)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_done[slot])
-                for n, t in outs.items():
-                    t.record_stream(self.s_out)
-                    self.hout[slot][n].copy_(t, non_blocking=True)
+                for task, stage in zip(rets, self.hout[slot]):
+                    for n, t in task.items():
+                        t.record_stream(self.s_out)
+                        stage[n].copy_(t, non_blocking=True)
                 self.ev_out[slot].record(self.s_out)
-            results.append(self.hout[slot])
-        cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_in)
+            pending[slot] = i
+        self.s_out.synchronize()                                    # every device->host copy has landed
+        self.s_in.synchronize()
+        for slot in (0, 1):
+            j = pending[slot]
+            if j is None:
+                continue
+            if on_result is not None:
+                on_result(j, self.hout[slot])
+            results[j] = self._collect(slot) if self.keep_results else self.hout[slot]
         return results
 
 

@@ -30,6 +30,7 @@ extern "C" {
 
 #define CMT_F32 0
 #define CMT_BF16 1
+#define CMT_F16 2       /* feature maps entering cmt_gather_tokens / cmt_nchw_to_padded_nhwc only */
 #define CMT_BF16_SIMT 3 /* cmt_cross_attn_fwd only: bf16 operands through the fp32 CUDA-core kernel (comparator) */
 
 /* flags of cmt_gemm_bias_act */
@@ -75,14 +76,18 @@ int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int
  * Replaces the rearrange + cat + repeat of CmtTransformer.forward
  * (models/utils/cmt_transformer.py:105-110) fused with `key = key + key_pos`
  * (models/utils/petr_transformer.py:296-299).
- * x_bev:   [B,C,n_bev] fp32 NCHW-flattened or NULL (n_bev = 0)
- * x_img:   [B*V,C,n_img] fp32 or NULL (V = 0)
+ * x_bev:   [B,C,n_bev] NCHW-flattened or NULL (n_bev = 0)
+ * x_img:   [B*V,C,n_img] or NULL (V = 0)
+ *          both in feat_dtype = CMT_F32 | CMT_BF16 | CMT_F16 (what the neck / backbone hands over; every feature
+ *          is rounded to out_dtype on arrival, so 16-bit features change no bit of the bf16 path)
  * bev_pos: [n_bev,C] fp32 (batch-invariant), rv_pos: [B*V*n_img,C] fp32
- * xk = mem + pos, xv = mem, both [B,N_kv,C] token-major, N_kv = n_bev + V*n_img,
- * order BEV tokens then image tokens view-major. out dtype fp32|bf16. */
-int cmt_gather_tokens(const float* x_bev, const float* x_img, const float* bev_pos,
+ * xk = mem + pos, xv = mem, token-major, order BEV tokens then image tokens view-major,
+ * N_kv = n_bev + V*n_img.  Only tokens [tok_begin, tok_end) are produced: xk, xv are
+ * [B, tok_end - tok_begin, C] (0, N_kv = everything; a sub-range = this rank's share of a KV-token
+ * split).  out dtype fp32|bf16. */
+int cmt_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                       const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                      int n_img, int out_dtype, void* stream);
+                      int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, void* stream);
 
 /* ---- K2: projection / MLP GEMM ------------------------------------------------------
  * C = act((A * B^T + bias) * alpha); A:[M,K] (lda), B:[N,K] (ldb), both row-major, K contiguous.
@@ -169,6 +174,15 @@ int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, co
 /* ---- cooperative V2I merge ----------------------------------------------------------
  * out = max(nan_to_num(a), nan_to_num(b)) element-wise (cmt_head_coop.py:358,383-389). */
 int cmt_coop_max(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+/* ---- diagnostics -----------------------------------------------------------------------
+ * Cycle accounting of the tcgen05 attention kernel on the CURRENT device.  dev_buf: device buffer of
+ * 3*96*16 + 148 int64 (or NULL to switch the hook off again).  While set, every CTA of every following
+ * cmt_cross_attn_fwd(bf16) launch on that device stores its total clock64 count into the last 148 entries
+ * (launch duration in SM cycles -> with an event time, the SM clock the kernel really ran at); a library built
+ * with -DCMT_ATTN_TRACE also fills the per-step stamps of CTA 0 (tools/attn_trace.py).  Not for production
+ * streams: the buffer pointer is process state, one slot per device. */
+int cmt_debug_attn_timing(void* dev_buf_i64);
 
 #ifdef __cplusplus
 }

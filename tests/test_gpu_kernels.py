@@ -96,6 +96,31 @@ def test_gather_tokens(case):
     assert torch.equal(xk16.cpu(), (mem + pos).permute(1, 0, 2).bfloat16())
 
 
+@pytest.mark.parametrize("fdt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("hw", [((9, 11), (5, 7)), ((10, 12), (6, 10))])   # odd / even token counts (scalar / paired loads)
+def test_gather_tokens_16bit_features_and_token_range(fdt, hw):
+    """Feature maps handed over in 16 bits (bf16 / fp16) and a token sub-range (KV-token split): bit-exact against the
+    oracle's rearrange + cat on the same (already rounded) feature values."""
+    (hb, wb), (hi_, wi) = hw
+    B, C, V = 2, 256, 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, hb, wb, generator=g).to(fdt)
+    xi = torch.randn(B * V, C, hi_, wi, generator=g).to(fdt)
+    n_bev, n_img = hb * wb, hi_ * wi
+    bev_pos = torch.randn(n_bev, C, generator=g)
+    rv_pos = torch.randn(B * V, hi_, wi, C, generator=g)
+    mem, pos = O.tokens(x.float(), xi.float(), bev_pos, rv_pos, B)
+    d = lambda t: t.to(DEV)
+    xk, xv = ops.gather_tokens(d(x), d(xi), d(bev_pos), d(rv_pos), B, V, out_dtype=torch.float32)
+    assert torch.equal(xv.cpu(), mem.permute(1, 0, 2)) and torch.equal(xk.cpu(), (mem + pos).permute(1, 0, 2))
+    n_kv = n_bev + V * n_img
+    for lo, hi in ((0, 64), (64, n_bev + 17), (n_bev - 3, n_kv), (n_bev + n_img, n_bev + n_img)):
+        xk16, xv16 = ops.gather_tokens(d(x), d(xi), d(bev_pos), d(rv_pos), B, V, out_dtype=torch.bfloat16, tok_range=(lo, hi))
+        assert xk16.shape == (B, hi - lo, C)
+        assert torch.equal(xv16.cpu(), mem.permute(1, 0, 2)[:, lo:hi].bfloat16())
+        assert torch.equal(xk16.cpu(), (mem + pos).permute(1, 0, 2)[:, lo:hi].bfloat16())
+
+
 def test_coop_max_and_lse_merge():
     a = torch.randn(3, 2, 50, 256)
     b = torch.randn(3, 2, 50, 256)

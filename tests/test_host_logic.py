@@ -138,3 +138,44 @@ def test_graph_runner_calibration_key():
     coop = [dict(vehicle_lidar2img=[np.eye(4)], infrastructure_lidar2img=[np.eye(4)] * 3)]
     coop2 = [dict(vehicle_lidar2img=[np.eye(4)], infrastructure_lidar2img=[np.eye(4)] * 2 + [2 * np.eye(4)])]
     assert _metas_key(coop) != _metas_key(coop2)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own configs (when the reference tree is present: this container, not the GPU box)
+REF_CONFIGS = "/root/reference/projects/configs"
+
+
+def _reference_config_files():
+    import glob
+    return sorted(glob.glob(os.path.join(REF_CONFIGS, "**", "*.py"), recursive=True))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason="reference tree not present")
+def test_every_reference_config_builds_its_head_unchanged():
+    """All 13 config files of the reference: exec the file (plain python dicts, no _base_ inheritance), take
+    model['pts_bbox_head'] with the detector's train/test cfg folded in exactly as MVXTwoStageDetector.__init__ does
+    (pts_bbox_head.update(train_cfg=train_cfg.pts, test_cfg=test_cfg.pts)), and build it through the plugin registry."""
+    files = _reference_config_files()
+    assert len(files) == 13, files
+    seen = set()
+    for f in files:
+        ns = {}
+        exec(compile(open(f).read(), f, "exec"), ns)
+        model = ns["model"]
+        head_cfg = dict(model["pts_bbox_head"])
+        test_cfg = model.get("test_cfg") or {}
+        head_cfg.update(train_cfg=None, test_cfg=test_cfg.get("pts"))
+        head = plugin.build_head(head_cfg)
+        assert type(head).__name__ == head_cfg["type"] and not head.training
+        seen.add(head_cfg["type"])
+        assert head.num_query == 900 and len(head.transformer.decoder.layers) == 6
+        n_bev = head.coords_bev.shape[0] if head._has_bev else 0
+        assert n_bev in (0, 128 * 128, 180 * 180), (f, n_bev)
+        # every cross-attention is the FlashMHA drop-in, state-dict keys are the reference's
+        for layer in head.transformer.decoder.layers:
+            assert isinstance(layer.attentions[1], plugin.PETRMultiheadFlashAttention)
+        sd = head.state_dict()
+        assert "reference_points.weight" in sd and "transformer.decoder.post_norm.weight" in sd
+        assert "transformer.decoder.layers.5.attentions.1.attn.in_proj_weight" in sd
+        assert ("shared_conv.conv.weight" in sd) == head._has_bev and ("rv_embedding.0.weight" in sd) == head._has_img
+    assert seen == set(synth.HEAD_KINDS)
