@@ -51,6 +51,8 @@ constexpr int THREADS = 384;  // 4 control warps + 8 epilogue warps
 #endif
 }  // namespace gemm
 
+constexpr int MAX_SEG = 18;
+
 struct TcGemmParams {
     const float* bias;
     void* C;
@@ -64,6 +66,21 @@ struct TcGemmParams {
     float* norm2_max; // [batch][N/32]: atomicMax of the squared norm of every row's 32-column block (attention score bound), or nullptr
     int transpose_c; // 1: element (m, n) of batch z is stored at z*strideC + (n / cb)*cb_stride + (n % cb)*ldc + m (bf16)
     int b_resident; // 1: gridDim.x = Gm * n_tiles, CTA c owns n-tile c % n_tiles and the (batch, m-tile) pairs c / n_tiles + i * Gm
+    // Segmented K (implicit convolutions and split-precision products): K block kb belongs to segment s = kb / kb_per_seg;
+    // its A tile is read at column seg_acol[s] + (kb % kb_per_seg) * BK and at row m0 + a_row_off + seg_shift[s] of the
+    // batch's A matrix (rows outside it are zero-filled by the TMA unit), while B is read at column kb * BK as usual.
+    // n_seg == 0: ordinary GEMM.
+    int n_seg, kb_per_seg, a_row_off;
+    int seg_acol[MAX_SEG], seg_shift[MAX_SEG];
+    int b_batch_div;   // batch z reads B of batch z / b_batch_div (task heads: one weight set per decoder layer, B frames each)
+    // Token epilogue of the 3x3 shared_conv (conv_xv != nullptr): output row m is position (y, x) = (m / conv_Wp, m % conv_Wp)
+    // of the zero-padded map of frame z; interior positions become token t = (y - 1) * conv_W + (x - 1) and are stored as
+    // xv[z][t - tok_begin] = bf16(v), xk[z][t - tok_begin] = bf16(v + pos[t]) (v = ReLU(acc + bias)); border rows are dropped.
+    void* conv_xk;
+    void* conv_xv;
+    const float* conv_pos;
+    int conv_W, conv_H, conv_Wp, conv_tok_begin, conv_tok_end;
+    long long conv_frame_stride;   // elements between frames in xk / xv
 };
 
 // The three roles walk the same tile sequence.
@@ -168,17 +185,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (; w.valid(); w.next()) {
                 int z, mt, nt;
                 w.decode(p, z, mt, nt);
+                const int zb = p.b_batched ? z / p.b_batch_div : 0;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    int acol = kb * BK, arow = mt * BM;
+                    if (p.n_seg > 0) {
+                        const int seg = kb / p.kb_per_seg;
+                        acol = p.seg_acol[seg] + (kb - seg * p.kb_per_seg) * BK;
+                        arow += p.a_row_off + p.seg_shift[seg];
+                    }
                     CMT_GEMM_WAIT(&empty_bar[stage], phase ^ 1);
                     if (leader) {
                         uint8_t* sa = ring + stage * ring_stride;
                         if (p.b_resident) {
                             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES);
-                            tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
+                            tma_load_3d(sa, &tma_a, &full_bar[stage], acol, arow, p.a_batched ? z : 0);
                         } else {
                             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                            tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, mt * BM, p.a_batched ? z : 0);
-                            tma_load_3d(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, nt * BN, p.b_batched ? z : 0);
+                            tma_load_3d(sa, &tma_a, &full_bar[stage], acol, arow, p.a_batched ? z : 0);
+                            tma_load_3d(sa + A_BYTES, &tma_b, &full_bar[stage], kb * BK, nt * BN, zb);
                         }
                     }
                     __syncwarp();
@@ -224,6 +248,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+        }
+    } else if (warp >= 4 && p.conv_xv != nullptr) {
+        // ------------------- epilogue of the 3x3 shared_conv: ReLU(acc + bias) -> token-major bf16 xv, xk = xv + pos -------------------
+        // (cmt_head.py:280-287,481 + cmt_transformer.py:105-110 + petr_transformer.py:296-299 for the BEV tokens: the NCHW
+        // fp32 map the reference writes and re-reads never exists.)  A thread owns one padded position and 32 consecutive
+        // channels per chunk: 64 contiguous bytes of each output row, 128 contiguous bytes of the position encoding.
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const uint32_t bias_addr = smem_u32(bias_s);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (TileWalk w(p); w.valid(); w.next()) {
+            int z, mt, nt;
+            w.decode(p, z, mt, nt);
+            const int m = mt * BM + quad * 32 + lane;
+            const int y = m / p.conv_Wp, x = m - y * p.conv_Wp;
+            const int tok = (y - 1) * p.conv_W + (x - 1);
+            const bool ok = m < p.M && y >= 1 && y <= p.conv_H && x >= 1 && x <= p.conv_W && tok >= p.conv_tok_begin && tok < p.conv_tok_end;
+            const long long orow = static_cast<long long>(z) * p.conv_frame_stride + static_cast<long long>(tok - p.conv_tok_begin) * p.N;
+            CMT_GEMM_WAIT(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int n_first = nt * BN + half * (BN / 2);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+            const int n_chunks = min(4, (p.N - n_first + 31) >> 5);
+            uint32_t v[2][32];
+            if (n_chunks > 0) {
+                tmem_ld32(t_row, v[0]);
+                tc_wait_ld();
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c >= n_chunks) break;
+                if (c + 1 < n_chunks) tmem_ld32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+                const int n0 = n_first + c * 32;
+                if (ok) {
+                    const uint32_t (&vc)[32] = v[c & 1];
+                    float f[32];
+                    const uint32_t baddr = bias_addr + n0 * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 b;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(baddr + i * 16));
+                        f[4 * i] = fmaxf(b.x + __uint_as_float(vc[4 * i]), 0.0f);
+                        f[4 * i + 1] = fmaxf(b.y + __uint_as_float(vc[4 * i + 1]), 0.0f);
+                        f[4 * i + 2] = fmaxf(b.z + __uint_as_float(vc[4 * i + 2]), 0.0f);
+                        f[4 * i + 3] = fmaxf(b.w + __uint_as_float(vc[4 * i + 3]), 0.0f);
+                    }
+                    uint8_t* dv = reinterpret_cast<uint8_t*>(p.conv_xv) + (orow + n0) * 2;
+                    uint8_t* dk = reinterpret_cast<uint8_t*>(p.conv_xk) + (orow + n0) * 2;
+                    const float4* pp = reinterpret_cast<const float4*>(p.conv_pos + static_cast<long long>(tok) * p.N + n0);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dv + 32 * i),
+                                     "r"(pack_bf16x2(f[16 * i + 0], f[16 * i + 1])), "r"(pack_bf16x2(f[16 * i + 2], f[16 * i + 3])),
+                                     "r"(pack_bf16x2(f[16 * i + 4], f[16 * i + 5])), "r"(pack_bf16x2(f[16 * i + 6], f[16 * i + 7])),
+                                     "r"(pack_bf16x2(f[16 * i + 8], f[16 * i + 9])), "r"(pack_bf16x2(f[16 * i + 10], f[16 * i + 11])),
+                                     "r"(pack_bf16x2(f[16 * i + 12], f[16 * i + 13])), "r"(pack_bf16x2(f[16 * i + 14], f[16 * i + 15]))
+                                     : "memory");
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 q = __ldg(pp + i);
+                        f[4 * i] += q.x; f[4 * i + 1] += q.y; f[4 * i + 2] += q.z; f[4 * i + 3] += q.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dk + 32 * i),
+                                     "r"(pack_bf16x2(f[16 * i + 0], f[16 * i + 1])), "r"(pack_bf16x2(f[16 * i + 2], f[16 * i + 3])),
+                                     "r"(pack_bf16x2(f[16 * i + 4], f[16 * i + 5])), "r"(pack_bf16x2(f[16 * i + 6], f[16 * i + 7])),
+                                     "r"(pack_bf16x2(f[16 * i + 8], f[16 * i + 9])), "r"(pack_bf16x2(f[16 * i + 10], f[16 * i + 11])),
+                                     "r"(pack_bf16x2(f[16 * i + 12], f[16 * i + 13])), "r"(pack_bf16x2(f[16 * i + 14], f[16 * i + 15]))
+                                     : "memory");
+                    }
+                }
+                if (c + 1 < n_chunks) tc_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4 && p.direct) {
         // ------------------- epilogue, lean path: registers -> 256-bit global stores -------------------

@@ -194,6 +194,8 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16,
     lo, hi = (0, N_kv) if tok_range is None else tok_range
     xk = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
     xv = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
+    if hi <= lo:
+        return xk, xv   # empty share of the token axis: nothing to launch
     lib = _lib.load()
     with torch.cuda.device(dev), _timed("gather_tokens", ref):
         rc = lib.cmt_gather_tokens(_ptr(x_bev), _ptr(x_img), _ptr(bev_pos), _ptr(rv_pos), _ptr(xk), _ptr(xv),
