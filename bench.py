@@ -52,13 +52,13 @@ WORKLOADS = {
 NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.394999e9 + 0.011791e9) / 8}
 
 
-def build_case(workload, B, seed=0):
+def build_case(workload, B, seed=0, in_channels=256):
     kind, bev_hw, n_views, _ = WORKLOADS[workload]
     cfg = synth.head_cfg(kind, num_query=900, num_layers=6, grid=8 * bev_hw)
     cfg["_apply_shared_conv"] = False
-    # hot-path scope: the BEV input is the post-shared_conv map (256 channels)
+    # hot-path scope: the BEV input is the post-shared_conv map (256 channels); in_channels=512: the raw map
     inputs = synth.make_inputs(kind, B=B, bev_hw=bev_hw, n_views=max(n_views, 1), img_hw=(40, 100),
-                               in_channels=256, seed=seed)
+                               in_channels=in_channels, seed=seed)
     return kind, cfg, inputs
 
 
@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the frame-0 oracle comparison (about 2 s of host work)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-shared-conv-leg", action="store_true", help="skip the second scope (step including shared_conv)")
     ap.add_argument("--kv-split", action="store_true",
                     help="BASELINE configs[4] variant: every rank sees the SAME frames and attends 1/N of the K/V tokens; "
                          "one NCCL all-gather of (O, LSE) per decoder layer + log-sum-exp merge (strong scaling)")
@@ -271,12 +272,13 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     metas = inputs["img_metas"]
 
-    def forward(feats):
+    def forward(feats, m=None):
         g = feats.get
+        m = metas if m is None else m
         if coop:
             return head.forward_single(g("vehicle_pts_feats"), g("infrastructure_pts_feats"), g("vehicle_img_feats"),
-                                       g("infrastructure_img_feats"), metas)
-        return head.forward_single(g("pts_feats"), g("img_feats"), metas)
+                                       g("infrastructure_img_feats"), m)
+        return head.forward_single(g("pts_feats"), g("img_feats"), m)
 
     def barrier():
         if world > 1:
@@ -373,6 +375,49 @@ def main():
             dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         ms_e2e = float(ms_t.item())
         h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+
+        # ---- second scope: the same step INCLUDING shared_conv (3x3 conv 512->256 + BN + ReLU on the raw BEV map,
+        # cmt_head.py:280-287,481) as the tcgen05 implicit GEMM that writes the BEV tokens ----
+        with_conv = None
+        if any("pts_feats" in k for k in feat_keys) and not kv_split and not args.no_shared_conv_leg:
+            kind2, _, inputs2 = build_case(args.workload, B, seed=rank, in_channels=512)
+            res2 = {k: torch.from_numpy(inputs2[k]).to(fdt).to(dev) for k in feat_keys}
+            metas2 = inputs2["img_metas"]
+            head.apply_shared_conv = True
+            for _ in range(3):
+                rets2 = forward(res2, metas2)
+            tags2 = ("shared_conv", "nchw_to_padded_nhwc")
+            for t in tags2:
+                ops.profile_events(t, True)
+            ms2_eager = timed(lambda: forward(res2, metas2), 5)
+            per2 = {t: ops.profile_events(t, False) for t in tags2}
+            ms2 = ms2_eager / 5 * args.steps
+            if not args.no_cuda_graph:
+                graphed2 = GraphedForward(head, metas2, res2, adopt_inputs=True)
+                for _ in range(3):
+                    rets2 = graphed2()
+                ms2 = timed(lambda: graphed2(), args.steps)
+            torch.cuda.synchronize()
+            par2 = None
+            if rank == 0 and not args.no_parity:
+                cfg2 = dict(cfg)
+                cfg2["_apply_shared_conv"] = True
+                par2 = parity_check(cfg2, inputs2, B, coop, fdt, head, rets2)
+            head.apply_shared_conv = False
+            n_conv = len(per2["shared_conv"]) // 5 if per2["shared_conv"] else 0     # launches per step (coop: one per node)
+            conv_ms = float(np.mean(per2["shared_conv"])) if per2["shared_conv"] else None
+            bev = inputs2[[k for k in feat_keys if "pts_feats" in k][0]]
+            conv_flops = 2.0 * B * bev.shape[2] * bev.shape[3] * 256 * 9 * 512
+            with_conv = dict(value=B * world * args.steps / (ms2 * 1e-3), unit="frames/s", ms_per_step=ms2 / args.steps,
+                             scope="forward_single from the RAW BEV map (512 channels) + image features: shared_conv included",
+                             parity=par2,
+                             shared_conv_kernel=dict(kernel="tc_gemm_kernel, 9-tap implicit GEMM + token epilogue", avg_launch_ms=conv_ms,
+                                                     launches_per_step=n_conv,
+                                                     achieved=(conv_flops / (conv_ms * 1e-3) / 1e12) if conv_ms else None, unit="TFLOP/s",
+                                                     frac=(conv_flops / (conv_ms * 1e-3) / 1e12 / peaks()["bf16_tflops_sustained"]) if conv_ms else None,
+                                                     algorithmic_flops_per_launch=conv_flops,
+                                                     layout_kernel_ms=float(np.mean(per2["nchw_to_padded_nhwc"])) if per2["nchw_to_padded_nhwc"] else None))
+            del res2
 
     frames = B * (1 if kv_split else world) * args.steps
     value = frames / (ms * 1e-3)
@@ -473,7 +518,7 @@ def main():
                     clocks=clocks, gpu_launches=launches,
                     e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
-                    parity=parity, roofline=roof, roofline_kernels=kernels, cpu_baseline=cpu)
+                    parity=parity, roofline=roof, roofline_kernels=kernels, with_shared_conv=with_conv, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
             print(f"bench.py: PARITY FAILED: frame 0 rel-L2 {parity['rel_l2']:.3e} > 1e-2", file=sys.stderr, flush=True)

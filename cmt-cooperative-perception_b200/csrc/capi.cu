@@ -228,6 +228,105 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
     return launch_simt_gemm(g, batch, in_dtype, s);
 }
 
+int cmt_gemm_segmented(const void* A, const void* B, const float* bias, void* C, int M, int N, int n_seg, int seg_k,
+                       const int* seg_acol_host, const int* seg_row_shift_host, int a_row_off, int64_t a_rows, int a_cols,
+                       int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB, int b_batch_div,
+                       int64_t strideC, float alpha, int flags, int out_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    CMT_CHECK_ARG(A && B && C && seg_acol_host && seg_row_shift_host, "cmt_gemm_segmented: null pointer");
+    CMT_CHECK_ARG(M > 0 && N > 0 && batch > 0 && n_seg > 0 && n_seg <= 18 && seg_k > 0, "cmt_gemm_segmented: bad shape");
+    CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gemm_segmented: bad out_dtype");
+    CMT_CHECK_ARG(!(flags & (CMT_GEMM_FORCE_SIMT | CMT_GEMM_TRANSPOSE_OUT)), "cmt_gemm_segmented: tensor-core path, plain output only");
+    GemmArgs g{};
+    g.A = A;
+    g.B = B;
+    g.bias = bias;
+    g.C = C;
+    g.M = M;
+    g.N = N;
+    g.K = n_seg * seg_k;
+    g.lda = lda;
+    g.ldb = ldb;
+    g.ldc = ldc;
+    g.cb = N;
+    g.cb_stride = 0;
+    g.strideA = strideA;
+    g.strideB = strideB;
+    g.strideC = strideC;
+    g.alpha = alpha;
+    g.relu = (flags & CMT_GEMM_RELU) ? 1 : 0;
+    g.bias_per_row = (flags & CMT_GEMM_BIAS_PER_ROW) ? 1 : 0;
+    g.out_bf16 = out_dtype == CMT_BF16;
+    g.n_seg = n_seg;
+    g.seg_k = seg_k;
+    g.a_row_off = a_row_off;
+    g.a_rows = a_rows;
+    g.a_cols = a_cols;
+    g.b_batch_div = b_batch_div;
+    for (int i = 0; i < n_seg; ++i) {
+        CMT_CHECK_ARG(seg_acol_host[i] >= 0 && seg_acol_host[i] % 8 == 0 && seg_acol_host[i] + seg_k <= a_cols,
+                      "cmt_gemm_segmented: segment %d reads columns [%d, %d) of %d", i, seg_acol_host[i], seg_acol_host[i] + seg_k, a_cols);
+        g.seg_acol[i] = seg_acol_host[i];
+        g.seg_shift[i] = seg_row_shift_host[i];
+    }
+    return launch_tc_gemm(g, batch, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, int W, int guard_rows, int in_dtype, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_nchw_to_padded_nhwc(x, out, B, C, H, W, guard_rows, in_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cmt_shared_conv_tokens(const void* xp, const void* w, const float* bias, const float* bev_pos, void* xk, void* xv, int B,
+                           int Cin, int Cout, int H, int W, int guard_rows, int64_t out_frame_stride, int tok_begin, int tok_end,
+                           void* stream) {
+    CMT_REQUIRE_DEVICE();
+    CMT_CHECK_ARG(xp && w && bias && bev_pos && xk && xv, "cmt_shared_conv_tokens: null pointer");
+    CMT_CHECK_ARG(B > 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 32 == 0 && H > 0 && W > 0 && guard_rows >= W + 3,
+                  "cmt_shared_conv_tokens: bad shape (Cin %% 64, Cout %% 32, guard_rows >= W + 3)");
+    CMT_CHECK_ARG(0 <= tok_begin && tok_begin < tok_end && tok_end <= H * W, "cmt_shared_conv_tokens: bad token range");
+    const int Wp = W + 2, Hp = H + 2;
+    const long long rows = 2ll * guard_rows + static_cast<long long>(Hp) * Wp;
+    GemmArgs g{};
+    g.A = xp;
+    g.B = w;
+    g.bias = bias;
+    g.C = xv;
+    g.M = Hp * Wp;
+    g.N = Cout;
+    g.K = 9 * Cin;
+    g.lda = Cin;
+    g.ldb = 9ll * Cin;
+    g.ldc = Cout;
+    g.cb = Cout;
+    g.strideA = rows * Cin;
+    g.strideB = 0;
+    g.strideC = 0;
+    g.alpha = 1.0f;
+    g.relu = 1;
+    g.out_bf16 = 1;
+    g.n_seg = 9;
+    g.seg_k = Cin;
+    g.a_row_off = guard_rows;
+    g.a_rows = rows;
+    g.a_cols = Cin;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            g.seg_acol[ky * 3 + kx] = 0;
+            g.seg_shift[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
+        }
+    g.conv_xk = xk;
+    g.conv_xv = xv;
+    g.conv_pos = bev_pos;
+    g.conv_W = W;
+    g.conv_H = H;
+    g.conv_Wp = Wp;
+    g.conv_tok_begin = tok_begin;
+    g.conv_tok_end = tok_end;
+    g.conv_frame_stride = out_frame_stride;
+    return launch_tc_gemm(g, B, static_cast<cudaStream_t>(stream));
+}
+
 size_t cmt_cross_attn_workspace_bytes(int B, int H, int Nq, int n_kv_tokens) {
     return tc_attn_workspace_bytes(B, H, Nq, n_kv_tokens);
 }

@@ -127,7 +127,7 @@ int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_
     CMT_CHECK_ARG(xk && xv, "cmt_gather_tokens: null output");
     CMT_CHECK_ARG(B > 0 && C > 0 && (C % 2) == 0, "cmt_gather_tokens: bad B/C");
     CMT_CHECK_ARG(n_bev >= 0 && V >= 0 && n_img >= 0, "cmt_gather_tokens: bad token counts");
-    CMT_CHECK_ARG(n_bev == 0 || (x_bev && bev_pos), "cmt_gather_tokens: BEV pointers missing");
+    CMT_CHECK_ARG(n_bev == 0 || x_bev == nullptr || bev_pos, "cmt_gather_tokens: BEV position encoding missing");
     CMT_CHECK_ARG(V == 0 || n_img == 0 || (x_img && rv_pos), "cmt_gather_tokens: image pointers missing");
     CMT_CHECK_ARG(out_dtype == CMT_F32 || out_dtype == CMT_BF16, "cmt_gather_tokens: bad output dtype");
     CMT_CHECK_ARG(feat_dtype == CMT_F32 || feat_dtype == CMT_BF16 || feat_dtype == CMT_F16, "cmt_gather_tokens: bad feature dtype");
@@ -137,7 +137,9 @@ int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_
                   tok_begin, tok_end, n_kv);
     CMT_CHECK_ARG(feat_dtype == CMT_F32 || ((reinterpret_cast<uintptr_t>(x_bev) | reinterpret_cast<uintptr_t>(x_img)) & 3) == 0,
                   "cmt_gather_tokens: 16-bit feature maps must be 4-byte aligned");
-    const int tiles_bev = (n_bev + kTileTok - 1) / kTileTok;
+    // x_bev == NULL with n_bev > 0: the BEV rows [0, n_bev) of xk / xv are produced elsewhere (the shared_conv epilogue,
+    // cmt_shared_conv_tokens); only the image tokens are gathered, at their usual row offset
+    const int tiles_bev = x_bev != nullptr ? (n_bev + kTileTok - 1) / kTileTok : 0;
     const int tiles_img = (n_img + kTileTok - 1) / kTileTok;
     const int tiles = tiles_bev + V * tiles_img;
     if (tiles == 0 || tok_begin == tok_end) return CMT_OK;
@@ -153,6 +155,70 @@ int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_
     else { if (ob) CMT_GATHER_LAUNCH(true, CMT_F16); else CMT_GATHER_LAUNCH(false, CMT_F16); }
 #undef CMT_GATHER_LAUNCH
     CMT_LAUNCH_CHECK("cmt_gather_tokens");
+    return CMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// NCHW feature map -> zero-padded, channel-last bf16 rows: the A operand of the 3x3 shared_conv implicit GEMM
+// (cmt_head.py:280-287,481).  Frame b occupies `rows_per_frame = 2 * guard + (H + 2) * (W + 2)` rows of C channels; pixel
+// (y, x) lands in row guard + (y + 1) * (W + 2) + (x + 1).  Only interior rows are written: the border and guard rows
+// are zero from the (one-time) allocation, so a filter tap is a pure row shift of -(W+2)-1 .. +(W+2)+1 with no edge
+// handling.  Block = 32 consecutive pixels x one block of up to 256 channels, same transpose tile as the token gather.
+template <int kIn>
+__global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                  int C, int H, int W, int guard, long long rows_per_frame) {
+    extern __shared__ float tile[];  // [32][257]
+    constexpr int ESZ = kIn == CMT_F32 ? 4 : 2;
+    constexpr int CB = 256, pitch = CB + 1;
+    const int b = blockIdx.y, c0 = blockIdx.z * CB;
+    const int nc = min(CB, C - c0);
+    const int n_src = H * W;
+    const int t0 = blockIdx.x * kTileTok;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + (static_cast<long long>(b) * C + c0) * n_src * ESZ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (kIn != CMT_F32 && (n_src & 1) == 0) {
+        const int half = lane >> 4, l16 = lane & 15;
+        const int tok = t0 + 2 * l16;
+        for (int c = 2 * warp + half; c < nc; c += 16) {
+            float lo = 0.0f, hi = 0.0f;
+            if (tok < n_src)
+                unpack_feat2<kIn>(__ldg(reinterpret_cast<const uint32_t*>(src + (static_cast<long long>(c) * n_src + tok) * 2)), lo, hi);
+            tile[(2 * l16) * pitch + c] = lo;
+            tile[(2 * l16 + 1) * pitch + c] = hi;
+        }
+    } else {
+        const int tok = t0 + lane;
+        const bool tok_ok = tok < n_src;
+        for (int c = warp; c < nc; c += 8)
+            tile[lane * pitch + c] = tok_ok ? load_feat<kIn>(src, static_cast<long long>(c) * n_src + tok) : 0.0f;
+    }
+    __syncthreads();
+    for (int r = warp; r < kTileTok; r += 8) {
+        const int st = t0 + r;
+        if (st >= n_src) break;
+        const int y = st / W, xx = st - y * W;
+        const long long row = static_cast<long long>(b) * rows_per_frame + guard + static_cast<long long>(y + 1) * (W + 2) + (xx + 1);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * C + c0);
+        const float* trow = tile + r * pitch;
+        for (int c = lane * 2; c < nc; c += 64) dst[c >> 1] = pack_bf16x2(trow[c], trow[c + 1]);
+    }
+}
+
+int launch_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, int W, int guard, int in_dtype,
+                               cudaStream_t stream) {
+    CMT_CHECK_ARG(x && out && B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && guard >= W + 3,
+                  "cmt_nchw_to_padded_nhwc: bad arguments (guard must be >= W + 3)");
+    CMT_CHECK_ARG(in_dtype == CMT_F32 || in_dtype == CMT_BF16 || in_dtype == CMT_F16, "cmt_nchw_to_padded_nhwc: bad dtype");
+    CMT_CHECK_ARG(B <= 65535, "cmt_nchw_to_padded_nhwc: batch too large");
+    CMT_CHECK_ARG(in_dtype == CMT_F32 || (reinterpret_cast<uintptr_t>(x) & 3) == 0, "cmt_nchw_to_padded_nhwc: unaligned input");
+    const long long rows = 2ll * guard + static_cast<long long>(H + 2) * (W + 2);
+    dim3 grid((H * W + kTileTok - 1) / kTileTok, B, (C + 255) / 256);
+    const size_t smem = static_cast<size_t>(kTileTok) * 257 * sizeof(float);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (in_dtype == CMT_F32) nchw_to_padded_nhwc_kernel<CMT_F32><<<grid, 256, smem, stream>>>(x, o, C, H, W, guard, rows);
+    else if (in_dtype == CMT_BF16) nchw_to_padded_nhwc_kernel<CMT_BF16><<<grid, 256, smem, stream>>>(x, o, C, H, W, guard, rows);
+    else nchw_to_padded_nhwc_kernel<CMT_F16><<<grid, 256, smem, stream>>>(x, o, C, H, W, guard, rows);
+    CMT_LAUNCH_CHECK("cmt_nchw_to_padded_nhwc");
     return CMT_OK;
 }
 

@@ -81,6 +81,7 @@ struct TcGemmParams {
     const float* conv_pos;
     int conv_W, conv_H, conv_Wp, conv_tok_begin, conv_tok_end;
     long long conv_frame_stride;   // elements between frames in xk / xv
+    int mt_off;                    // first m-tile (conv with a token sub-range computes only the rows that hold its tokens)
 };
 
 // The three roles walk the same tile sequence.
@@ -113,6 +114,7 @@ struct TileWalk {
             mt = r / p.n_tiles;
             nt = r - mt * p.n_tiles;
         }
+        mt += p.mt_off;
     }
 };
 
@@ -592,6 +594,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     using namespace gemm;
+    CMT_CHECK_ARG(g.n_seg >= 0 && g.n_seg <= MAX_SEG, "cmt_gemm(bf16): at most %d K segments", MAX_SEG);
+    CMT_CHECK_ARG(g.n_seg == 0 || (g.seg_k > 0 && g.seg_k % BK == 0 && g.K == g.n_seg * g.seg_k && g.a_cols > 0 && g.a_rows > 0),
+                  "cmt_gemm(bf16): segmented K needs seg_k %% %d == 0 and K == n_seg * seg_k", BK);
     CMT_CHECK_ARG(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0,
                   "cmt_gemm_bias_act(bf16): K, lda, ldb must be multiples of 8 (K=%d lda=%lld ldb=%lld)",
                   g.K, g.lda, g.ldb);
@@ -613,18 +618,20 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     CUtensorMap ta, tb;
     {
         const bool batched = g.strideA != 0 && batch > 1;
-        uint64_t dims[3] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.M),
+        const long long a_rows = g.n_seg > 0 ? g.a_rows : g.M;
+        uint64_t dims[3] = {static_cast<uint64_t>(g.n_seg > 0 ? g.a_cols : g.K), static_cast<uint64_t>(a_rows),
                             static_cast<uint64_t>(batched ? batch : 1)};
         uint64_t strides[2] = {static_cast<uint64_t>(g.lda) * 2,
-                               static_cast<uint64_t>(batched ? g.strideA : (long long)g.M * g.lda) * 2};
+                               static_cast<uint64_t>(batched ? g.strideA : a_rows * g.lda) * 2};
         uint32_t box[3] = {BK, BM, 1};
         int rc = encode_tma_bf16(&ta, g.A, 3, dims, strides, box, 128);
         if (rc) return rc;
     }
     {
         const bool batched = g.strideB != 0 && batch > 1;
+        const int b_div = g.b_batch_div > 1 ? g.b_batch_div : 1;
         uint64_t dims[3] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.N),
-                            static_cast<uint64_t>(batched ? batch : 1)};
+                            static_cast<uint64_t>(batched ? (batch + b_div - 1) / b_div : 1)};
         uint64_t strides[2] = {static_cast<uint64_t>(g.ldb) * 2,
                                static_cast<uint64_t>(batched ? g.strideB : (long long)g.N * g.ldb) * 2};
         uint32_t box[3] = {BK, BN, 1};
@@ -638,6 +645,28 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     TcGemmParams p{};
     p.transpose_c = g.transpose_c;
     p.norm2_max = g.norm2_max;
+    p.n_seg = g.n_seg;
+    p.kb_per_seg = g.n_seg > 0 ? g.seg_k / BK : 0;
+    p.a_row_off = g.a_row_off;
+    for (int i = 0; i < g.n_seg; ++i) {
+        p.seg_acol[i] = g.seg_acol[i];
+        p.seg_shift[i] = g.seg_shift[i];
+    }
+    p.b_batch_div = g.b_batch_div > 1 ? g.b_batch_div : 1;
+    p.conv_xk = g.conv_xk;
+    p.conv_xv = g.conv_xv;
+    p.conv_pos = g.conv_pos;
+    p.conv_W = g.conv_W;
+    p.conv_H = g.conv_H;
+    p.conv_Wp = g.conv_Wp;
+    p.conv_tok_begin = g.conv_tok_begin;
+    p.conv_tok_end = g.conv_tok_end;
+    p.conv_frame_stride = g.conv_frame_stride;
+    if (g.conv_xv != nullptr)
+        CMT_CHECK_ARG(g.conv_xk && g.conv_pos && g.bias && !g.bias_per_row && g.N % 32 == 0 && g.N <= BIAS_CAP - 64 &&
+                          (reinterpret_cast<uintptr_t>(g.conv_xk) & 31) == 0 && (reinterpret_cast<uintptr_t>(g.conv_xv) & 31) == 0 &&
+                          (reinterpret_cast<uintptr_t>(g.conv_pos) & 15) == 0 && g.conv_frame_stride % 16 == 0,
+                      "cmt_shared_conv_tokens: bias, pos, 32-byte aligned outputs and N %% 32 == 0 required");
     static const bool no_direct = getenv("CMT_GEMM_NO_DIRECT") != nullptr;
     const bool bias_ok = g.bias == nullptr || g.bias_per_row || g.N <= BIAS_CAP - 64;
     if (g.transpose_c) {
@@ -669,6 +698,13 @@ int launch_tc_gemm(const GemmArgs& g, int batch, cudaStream_t stream) {
     p.b_batched = (g.strideB != 0 && batch > 1) ? 1 : 0;
     p.m_tiles = (g.M + BM - 1) / BM;
     p.n_tiles = (g.N + BN - 1) / BN;
+    if (g.conv_xv != nullptr) {
+        // only the m-tiles whose padded rows hold tokens of [tok_begin, tok_end)
+        const int y_lo = g.conv_tok_begin / g.conv_W, y_hi = (g.conv_tok_end - 1) / g.conv_W;
+        const int p_lo = (y_lo + 1) * g.conv_Wp + 1, p_hi = (y_hi + 1) * g.conv_Wp + g.conv_W + 1;   // [p_lo, p_hi)
+        p.mt_off = p_lo / BM;
+        p.m_tiles = (p_hi + BM - 1) / BM - p.mt_off;
+    }
     const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * batch;
     CMT_CHECK_ARG(total < (1ll << 31), "cmt_gemm_bias_act(bf16): too many tiles");
     p.total_tiles = static_cast<int>(total);

@@ -16,6 +16,20 @@ struct GemmArgs {
     int relu, bias_per_row, out_bf16;
     int transpose_c;   // bf16 tensor-core path only: store C^T inside each column block (see cmt_gemm_bias_act)
     float* norm2_max;  // bf16 tensor-core path only: [batch][N/32] running max of the squared row norms per 32-column block, or nullptr
+    // ---- bf16 tensor-core path only: segmented K (n_seg == 0: ordinary GEMM) ----
+    // K = n_seg * seg_k columns of B; segment s multiplies B[:, s*seg_k : (s+1)*seg_k] with the A columns
+    // [seg_acol[s], seg_acol[s] + seg_k) read at row (m + a_row_off + seg_shift[s]) of the batch's A matrix, which has
+    // a_rows rows and a_cols columns (rows outside [0, a_rows) read as zero).
+    int n_seg, seg_k, a_row_off, a_cols;
+    long long a_rows;
+    int seg_acol[18], seg_shift[18];
+    int b_batch_div;   // batch z uses B of batch z / b_batch_div (0 or 1: z)
+    // ---- token epilogue of the 3x3 shared_conv (conv_xv != nullptr), see TcGemmParams ----
+    void* conv_xk;
+    void* conv_xv;
+    const float* conv_pos;
+    int conv_W, conv_H, conv_Wp, conv_tok_begin, conv_tok_end;
+    long long conv_frame_stride;
 };
 
 struct AttnArgs {
@@ -47,6 +61,8 @@ int launch_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, 
 int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                          const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
                          int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, cudaStream_t stream);
+int launch_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, int W, int guard, int in_dtype,
+                               cudaStream_t stream);
 int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
                      int B, int H, int Nq, int o_dtype, cudaStream_t stream);

@@ -165,7 +165,8 @@ def pos2embed(pos, num_pos_feats=128, out_dtype=torch.bfloat16):
 _FEAT_DTYPES = {torch.float32: CMT_F32, torch.bfloat16: CMT_BF16, torch.float16: CMT_F16}
 
 
-def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16, tok_range=None):
+def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16, tok_range=None, n_bev_reserved=0,
+                  out=None):
     """K4 (cmt_transformer.py:105-110 + petr_transformer.py:296-299).
     x_bev [B,C,Hb,Wb] | None, x_img [B*V,C,h,w] | None (fp32, bf16 or fp16 -- both the same dtype),
     bev_pos [N_bev,C], rv_pos [B*V*h*w, C] (any leading shape) fp32 -> xk = mem+pos, xv = mem, both
@@ -190,10 +191,16 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16,
         assert x_img.shape[0] == B * V and rv_pos.numel() == B * V * n_img * C
     else:
         V = 0
+    if x_bev is None:
+        n_bev = n_bev_reserved
     N_kv = n_bev + V * n_img
     lo, hi = (0, N_kv) if tok_range is None else tok_range
-    xk = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
-    xv = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
+    if out is not None:
+        xk, xv = out
+        assert xk.shape == (B, hi - lo, C) and xv.shape == xk.shape and xk.dtype == out_dtype and xk.is_contiguous()
+    else:
+        xk = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
+        xv = torch.empty((B, hi - lo, C), dtype=out_dtype, device=dev)
     if hi <= lo:
         return xk, xv   # empty share of the token axis: nothing to launch
     lib = _lib.load()
@@ -203,6 +210,77 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16,
     _lib.check(rc, "cmt_gather_tokens")
     _count()
     return xk, xv
+
+
+def conv_guard_rows(W):
+    """Guard rows before and after each frame of the padded channel-last operand (>= W + 3, kept a multiple of 8)."""
+    return (W + 3 + 7) // 8 * 8
+
+
+def nchw_to_padded_nhwc(x, out=None):
+    """[B,C,H,W] (fp32|bf16|fp16) -> zero-padded channel-last bf16 rows [B, 2*guard + (H+2)*(W+2), C] (cmt_nchw_to_padded_nhwc).
+    `out` (zero-initialised once, then reusable: only interior rows are written) is allocated when None."""
+    x = _cuda(x, "x")
+    if x.dtype not in _FEAT_DTYPES:
+        raise TypeError(f"feature maps must be fp32, bf16 or fp16, got {x.dtype}")
+    B, C, H, W = x.shape
+    guard = conv_guard_rows(W)
+    rows = 2 * guard + (H + 2) * (W + 2)
+    if out is None:
+        out = torch.zeros((B, rows, C), dtype=torch.bfloat16, device=x.device)
+    assert out.shape == (B, rows, C) and out.dtype == torch.bfloat16 and out.is_contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(x.device), _timed("nchw_to_padded_nhwc", x):
+        rc = lib.cmt_nchw_to_padded_nhwc(_ptr(x), _ptr(out), B, C, H, W, guard, _FEAT_DTYPES[x.dtype], _stream(x))
+    _lib.check(rc, "cmt_nchw_to_padded_nhwc")
+    _count()
+    return out
+
+
+def shared_conv_tokens(xp, w, bias, bev_pos, xk, xv, H, W, tok_range=None):
+    """3x3 conv + folded BN + ReLU as an implicit GEMM writing the BEV token rows of xk / xv (cmt_shared_conv_tokens).
+    xp [B,rows,Cin] from nchw_to_padded_nhwc; w [Cout, 9*Cin] bf16 tap-major with the BN scale folded in; bias [Cout] fp32;
+    bev_pos [H*W,Cout] fp32; xk, xv [B,n_rows,Cout] bf16 whose first (hi-lo) rows receive tokens [lo,hi) (default all)."""
+    xp = _cuda(xp, "xp", torch.bfloat16)
+    w = _cuda(w, "w", torch.bfloat16)
+    bias = _cuda(bias, "bias", torch.float32)
+    bev_pos = _cuda(bev_pos, "bev_pos", torch.float32)
+    xk = _cuda(xk, "xk", torch.bfloat16)
+    xv = _cuda(xv, "xv", torch.bfloat16)
+    B, rows, Cin = xp.shape
+    Cout = w.shape[0]
+    guard = conv_guard_rows(W)
+    assert rows == 2 * guard + (H + 2) * (W + 2) and w.shape[1] == 9 * Cin and bev_pos.numel() == H * W * Cout
+    lo, hi = (0, H * W) if tok_range is None else tok_range
+    assert xk.shape[0] == B and xk.shape[2] == Cout and xk.shape[1] >= hi - lo and xv.shape == xk.shape
+    lib = _lib.load()
+    with torch.cuda.device(xp.device), _timed("shared_conv", xp):
+        rc = lib.cmt_shared_conv_tokens(_ptr(xp), _ptr(w), _ptr(bias), _ptr(bev_pos), _ptr(xk), _ptr(xv), B, Cin, Cout, H, W,
+                                        guard, xk.shape[1] * Cout, lo, hi, _stream(xp))
+    _lib.check(rc, "cmt_shared_conv_tokens")
+    _count()
+
+
+def gemm_segmented(A, Bm, bias, C, M, N, seg_k, seg_acol, seg_shift, *, a_row_off, a_rows, a_cols, lda, ldb, ldc, batch=1,
+                   strideA=0, strideB=0, b_batch_div=1, strideC=0, alpha=1.0, relu=False, tag=None):
+    """cmt_gemm_segmented: C[z] = act((sum_s A_z[m + a_row_off + shift_s, acol_s : acol_s + seg_k] . B_zb[n, s*seg_k : ...] + bias) alpha)."""
+    A = _cuda(A, "A", torch.bfloat16)
+    Bm = _cuda(Bm, "B", torch.bfloat16)
+    C = _cuda(C, "C")
+    if bias is not None:
+        bias = _cuda(bias, "bias", torch.float32)
+    n_seg = len(seg_acol)
+    assert len(seg_shift) == n_seg
+    acol = (ctypes.c_int * n_seg)(*[int(v) for v in seg_acol])
+    shift = (ctypes.c_int * n_seg)(*[int(v) for v in seg_shift])
+    lib = _lib.load()
+    with torch.cuda.device(A.device), _timed(tag, A):
+        rc = lib.cmt_gemm_segmented(_ptr(A), _ptr(Bm), _ptr(bias), _ptr(C), M, N, n_seg, seg_k, ctypes.cast(acol, ctypes.c_void_p),
+                                    ctypes.cast(shift, ctypes.c_void_p), a_row_off, a_rows, a_cols, lda, ldb, ldc, batch, strideA,
+                                    strideB, b_batch_div, strideC, float(alpha), GEMM_RELU if relu else 0, _dt(C.dtype), _stream(A))
+    _lib.check(rc, "cmt_gemm_segmented")
+    _count()
+    return C
 
 
 def gemm(A, Bm, bias, C, M, N, K, *, lda, ldb, ldc, cb=None, cb_stride=0, batch=1, strideA=0, strideB=0,

@@ -229,6 +229,9 @@ class _CmtHeadBase(nn.Module):
         self.precision = "bf16"
         # bench.py times "CmtTransformer+PE" from the post-shared_conv BEV map; set False then
         self.apply_shared_conv = True
+        # bf16 mode: shared_conv runs as a tcgen05 implicit GEMM whose epilogue writes the BEV token rows directly
+        # (cmt_shared_conv_tokens); False keeps torch's Conv2d + BatchNorm2d + ReLU (always used in fp32 mode)
+        self.fuse_shared_conv = True
 
         self.shared_conv = _ConvModule(in_channels, hidden_dim, 3, 1) if self._has_bev else None
         transformer = ConfigDict(copy.deepcopy(transformer))
@@ -298,6 +301,36 @@ class _CmtHeadBase(nn.Module):
         dt = _compute_dtype(self.precision)
         h = ops.linear(x.to(dt), w0, b0, relu=True, out_dtype=dt, tag=None if tag is None else tag + ".0")
         return ops.linear(h, w1, b1, out_dtype=torch.float32, tag=None if tag is None else tag + ".2")
+
+    # -- shared_conv (cmt_head.py:280-287, applied :481) -------------------------------------
+    def _shared_conv_folded(self):
+        """conv weight with the eval-mode BatchNorm scale folded in, tap-major [Cout, 9*Cin] bf16, and the remaining
+        per-channel bias: BN(conv(x)) = conv(x; w * s) + (beta - mean * s), s = gamma / sqrt(var + eps)."""
+        conv, bn = self.shared_conv.conv, self.shared_conv.bn
+        key = ("conv", conv.weight._version, conv.weight.data_ptr(), bn.weight._version, bn.bias._version,
+               bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr())
+        hit = self._cache.get("shared_conv")
+        if hit is None or hit[0] != key:
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = conv.weight.detach().float() * s[:, None, None, None]                  # [Cout, Cin, 3, 3]
+            w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()   # [Cout, (ky, kx, c)]
+            b = (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
+            hit = (key, (w, b))
+            self._cache["shared_conv"] = hit
+        return hit[1]
+
+    def _apply_shared_conv_to(self, x):
+        """The BEV map the transformer consumes: the input itself (bench scope), a BevTokenSource for the fused
+        implicit-GEMM path (bf16 mode), or torch's conv + BN + ReLU in fp32."""
+        if not self.apply_shared_conv:
+            return x
+        conv = self.shared_conv.conv
+        if (self.precision == "bf16" and self.fuse_shared_conv and conv.kernel_size == (3, 3) and conv.in_channels % 64 == 0
+                and conv.out_channels % 32 == 0):
+            from .cmt_transformer import BevTokenSource
+            w, b = self._shared_conv_folded()
+            return BevTokenSource(x, w, b)
+        return self.shared_conv(x.float())
 
     # -- position encodings -----------------------------------------------------------------
     def _matrices(self, img_metas, device):
@@ -375,12 +408,12 @@ class _CmtHeadBase(nn.Module):
         bev_q, rv_q = self.query_embed(reference_points, img_metas, mats)
         query_embeds = bev_q if rv_q is None else bev_q + rv_q
         if self._has_bev and self._has_img:
-            x = self.shared_conv(x) if self.apply_shared_conv else x
+            x = self._apply_shared_conv_to(x)
             rv_pos = self._rv_pe(x_img, img_metas, mats)
             outs_dec, _ = self.transformer(x, x_img, query_embeds, self._bev_pos_embed(dev), rv_pos,
                                            attn_masks=attn_mask)
         elif self._has_bev:
-            x = self.shared_conv(x) if self.apply_shared_conv else x
+            x = self._apply_shared_conv_to(x)
             mask = None
             outs_dec, _ = self.transformer(x, mask, query_embeds, self._bev_pos_embed(dev), attn_masks=attn_mask)
         else:

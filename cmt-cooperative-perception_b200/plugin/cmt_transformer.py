@@ -22,6 +22,24 @@ def _compute_dtype(precision):
     return torch.float32 if precision == "fp32" else torch.bfloat16
 
 
+class BevTokenSource:
+    """The BEV map BEFORE shared_conv together with the folded conv + BN parameters: handed to the transformer in place
+    of the convolved [B,C,H,W] tensor so that the 3x3 convolution runs as a tcgen05 implicit GEMM whose epilogue writes
+    the BEV token rows of xk / xv directly (cmt_head.py:280-287,481 fused with cmt_transformer.py:105-110 and
+    petr_transformer.py:296-299).  Quacks like the tensor as far as the transformer's forward signature needs."""
+
+    def __init__(self, x_raw, w, bias):
+        self.x = x_raw                      # [B, Cin, H, W] fp32 | bf16 | fp16
+        self.w = w                          # [Cout, 9*Cin] bf16, tap-major, BN scale folded in
+        self.bias = bias                    # [Cout] fp32
+        self.shape = (x_raw.shape[0], w.shape[0], x_raw.shape[2], x_raw.shape[3])
+        self.device = x_raw.device
+
+    def contiguous(self):
+        self.x = self.x.contiguous()
+        return self
+
+
 class _CmtTransformerBase(nn.Module):
     def __init__(self, encoder=None, decoder=None, init_cfg=None, cross=False):
         super().__init__()
@@ -33,6 +51,7 @@ class _CmtTransformerBase(nn.Module):
         self.kv_split_group = None
         self.use_fused_decoder = True  # False: module-by-module path (torch self-attention / LN / FFN)
         self._kv_w = None
+        self._xp = None
         self._is_init = False
 
     def init_weights(self):
@@ -101,8 +120,26 @@ class _CmtTransformerBase(nn.Module):
         if hi <= lo:   # more ranks than token tiles: this rank contributes the neutral element of the merge
             return KVCache(None, None, 0, group), None
         # with the split, the gather kernel itself produces only the rank's rows: K1/K4/K2 all shard with the tokens
-        xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt,
-                                   tok_range=None if group is None else (lo, hi))
+        if isinstance(x_bev, BevTokenSource):
+            Hb, Wb = x_bev.shape[2], x_bev.shape[3]
+            n_bev = Hb * Wb
+            C = x_bev.shape[1]
+            dev = x_bev.device
+            xk = torch.empty((B, hi - lo, C), dtype=dt, device=dev)
+            xv = torch.empty((B, hi - lo, C), dtype=dt, device=dev)
+            key = (tuple(x_bev.x.shape), str(dev))
+            if self._xp is None or self._xp[0] != key:   # zero-padded channel-last operand: zeroed once, interior rewritten per call
+                self._xp = (key, ops.nchw_to_padded_nhwc(x_bev.x))
+            else:
+                ops.nchw_to_padded_nhwc(x_bev.x, self._xp[1])
+            if lo < n_bev:
+                ops.shared_conv_tokens(self._xp[1], x_bev.w, x_bev.bias, bev_pos, xk, xv, Hb, Wb, tok_range=(lo, min(hi, n_bev)))
+            if x_img is not None and hi > n_bev:
+                ops.gather_tokens(None, x_img, None, rv_pos, B, V, out_dtype=dt, tok_range=(lo, hi), n_bev_reserved=n_bev,
+                                  out=(xk, xv))
+        else:
+            xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt,
+                                       tok_range=None if group is None else (lo, hi))
         wk, bk, wv, bv = self._stacked_kv_weights()
         kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
         k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)

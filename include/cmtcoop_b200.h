@@ -76,7 +76,8 @@ int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int
  * Replaces the rearrange + cat + repeat of CmtTransformer.forward
  * (models/utils/cmt_transformer.py:105-110) fused with `key = key + key_pos`
  * (models/utils/petr_transformer.py:296-299).
- * x_bev:   [B,C,n_bev] NCHW-flattened or NULL (n_bev = 0)
+ * x_bev:   [B,C,n_bev] NCHW-flattened, or NULL (n_bev = 0: no BEV tokens; n_bev > 0: rows [0,n_bev) of xk / xv are
+ *          produced by cmt_shared_conv_tokens and only the image tokens are gathered, at row offset n_bev)
  * x_img:   [B*V,C,n_img] or NULL (V = 0)
  *          both in feat_dtype = CMT_F32 | CMT_BF16 | CMT_F16 (what the neck / backbone hands over; every feature
  *          is rounded to out_dtype on arrival, so 16-bit features change no bit of the bf16 path)
@@ -112,6 +113,38 @@ int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, 
                       int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t cb, int64_t cb_stride,
                       int batch, int64_t strideA, int64_t strideB, int64_t strideC, float alpha,
                       int flags, int in_dtype, int out_dtype, float* norm2_max, void* stream);
+
+/* Segmented-K form of cmt_gemm_bias_act (bf16 operands, tensor-core path, plain row-major output):
+ *     C[z][m][n] = act((sum_s sum_k A_z[m + a_row_off + row_shift[s]][acol[s] + k] * B_zb[n][s*seg_k + k] + bias[n]) * alpha)
+ * for s < n_seg <= 18, k < seg_k (a multiple of 64), zb = z / b_batch_div.  A_z is the [a_rows, a_cols] matrix at
+ * A + z*strideA (row stride lda); rows outside [0, a_rows) read as zero.  One mechanism, two uses: implicit convolutions
+ * (a filter tap = a row shift of a channel-last operand: the k = 3 task-head convolutions over the query axis,
+ * cmt_head.py:116-150, and the 3x3 shared_conv below) and split-precision products (A = [hi | mid | lo] bf16 terms of an
+ * fp32 operand, segments pairing them with the matching terms of the weights: fp32-grade task-head logits on the tensor
+ * cores).  seg_acol / seg_row_shift are HOST arrays of n_seg ints. */
+int cmt_gemm_segmented(const void* A, const void* B, const float* bias, void* C, int M, int N, int n_seg, int seg_k,
+                       const int* seg_acol_host, const int* seg_row_shift_host, int a_row_off, int64_t a_rows,
+                       int a_cols, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB,
+                       int b_batch_div, int64_t strideC, float alpha, int flags, int out_dtype, void* stream);
+
+/* ---- shared_conv: 3x3 conv 512->256 + BatchNorm(eval) + ReLU as an implicit GEMM writing BEV tokens ----------------
+ * Replaces ConvModule(conv3x3 no bias, BN2d, ReLU) of CmtHead (models/dense_heads/cmt_head.py:280-287, applied :481,
+ * coop: cmt_head_coop.py:343) TOGETHER with the BEV half of the token rearrange / pos add
+ * (models/utils/cmt_transformer.py:105-110, petr_transformer.py:296-299): the NCHW fp32 map never exists.
+ * Step 1, cmt_nchw_to_padded_nhwc: x [B,C,H,W] (fp32|bf16|fp16) -> out bf16 [B][2*guard_rows + (H+2)*(W+2)][C], pixel
+ *   (y,x) in row guard_rows + (y+1)*(W+2) + (x+1); only interior rows are written (the caller zero-fills `out` once),
+ *   guard_rows >= W + 3.
+ * Step 2, cmt_shared_conv_tokens: w bf16 [Cout][9*Cin], tap-major (w[o][(ky*3+kx)*Cin + c] = conv.weight[o][c][ky][kx] *
+ *   bn_scale[o]), bias fp32 [Cout] = bn.bias - bn.running_mean * bn_scale, bev_pos fp32 [H*W, Cout];
+ *   for every frame b and token t = y*W + x in [tok_begin, tok_end):
+ *     v = ReLU(conv(x)[b,:,y,x] + bias);  xv[b][t - tok_begin][:] = bf16(v);  xk[b][t - tok_begin][:] = bf16(v + bev_pos[t])
+ *   with out_frame_stride elements between frames (N_kv * Cout: the image tokens follow, cmt_gather_tokens with
+ *   x_bev = NULL).  Cin % 64 == 0, Cout % 32 == 0, Cout <= 1984. */
+int cmt_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, int W, int guard_rows, int in_dtype,
+                            void* stream);
+int cmt_shared_conv_tokens(const void* xp, const void* w, const float* bias, const float* bev_pos, void* xk, void* xv,
+                           int B, int Cin, int Cout, int H, int W, int guard_rows, int64_t out_frame_stride,
+                           int tok_begin, int tok_end, void* stream);
 
 /* ---- K3: flash cross-attention ------------------------------------------------------
  * Replaces flash_attn_unpadded_kvpacked_func as called by FlashAttention.forward

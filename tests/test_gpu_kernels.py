@@ -121,6 +121,98 @@ def test_gather_tokens_16bit_features_and_token_range(fdt, hw):
         assert torch.equal(xk16.cpu(), (mem + pos).permute(1, 0, 2)[:, lo:hi].bfloat16())
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 64, 9, 11, torch.float32), (1, 64, 32, 5, 4, torch.bfloat16),
+                                   (1, 512, 256, 180, 180, torch.bfloat16)])
+def test_shared_conv_tokens(shape):
+    """3x3 conv + folded BN + ReLU as a tcgen05 implicit GEMM writing token-major xv and xk = xv + pos
+    (cmt_head.py:280-287,481): against conv2d on the same bf16-rounded operands (fp64 for the small cases), token
+    indexing t = y*W + x, then the token sub-range form (KV-token split) and the image tokens appended by the gather."""
+    import torch.nn.functional as F
+    B, Cin, Cout, H, W, fdt = shape
+    g = torch.Generator().manual_seed(H * W + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g).to(fdt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    pos = torch.randn(H * W, Cout, generator=g)
+    wt = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).bfloat16()
+    big = H * W > 1000
+    ref_dt = torch.float32 if big else torch.float64
+    xr = x.bfloat16().to(ref_dt)
+    wr = wt.to(ref_dt).view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    want = F.relu(F.conv2d(xr, wr, bias.to(ref_dt), padding=1)).flatten(2).transpose(1, 2)     # [B, H*W, Cout]
+    d = lambda t: t.to(DEV)
+    xp = ops.nchw_to_padded_nhwc(d(x))
+    guard = ops.conv_guard_rows(W)
+    # bit-exact layout of the padded operand: interior = bf16(x), everything else zero
+    xpc = xp.cpu().float()
+    inner = xpc[:, guard:guard + (H + 2) * (W + 2)].view(B, H + 2, W + 2, Cin)
+    assert torch.equal(inner[:, 1:-1, 1:-1], x.bfloat16().float().permute(0, 2, 3, 1))
+    assert float(xpc.abs().sum()) == float(inner[:, 1:-1, 1:-1].abs().sum())
+    n_extra = 7
+    xk = torch.full((B, H * W + n_extra, Cout), 7.0, dtype=torch.bfloat16, device=DEV)
+    xv = torch.full((B, H * W + n_extra, Cout), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.shared_conv_tokens(xp, d(wt), d(bias), d(pos), xk, xv, H, W)
+    torch.cuda.synchronize()
+    assert _rel(xv[:, :H * W].float(), want) < 4e-3
+    assert _rel(xk[:, :H * W].float(), want + pos.to(ref_dt)) < 4e-3
+    assert bool((xv[:, H * W:] == 7.0).all()) and bool((xk[:, H * W:] == 7.0).all())     # rows past the BEV tokens untouched
+    # xk is one rounding of (fp32 value + pos): consistent with xv up to its own rounding
+    assert ((xk[:, :H * W].float().cpu() - (xv[:, :H * W].float().cpu() + pos)).abs() <=
+            0.01 * (xv[:, :H * W].float().cpu().abs() + pos.abs()) + 1e-6).all()
+    # token sub-range: same values, row 0 = token lo
+    lo, hi = (W + 3, H * W - 2 * W - 1)
+    xk2 = torch.zeros((B, hi - lo, Cout), dtype=torch.bfloat16, device=DEV)
+    xv2 = torch.zeros_like(xk2)
+    ops.shared_conv_tokens(xp, d(wt), d(bias), d(pos), xk2, xv2, H, W, tok_range=(lo, hi))
+    assert torch.equal(xv2, xv[:, lo:hi]) and torch.equal(xk2, xk[:, lo:hi])
+    # the padded buffer is reusable: a second, different input through the same buffer
+    x2 = (x.float() * 0.5 + 0.25).to(fdt)
+    ops.nchw_to_padded_nhwc(d(x2), xp)
+    ops.shared_conv_tokens(xp, d(wt), d(bias), d(pos), xk, xv, H, W)
+    want2 = F.relu(F.conv2d(x2.bfloat16().to(ref_dt), wr, bias.to(ref_dt), padding=1)).flatten(2).transpose(1, 2)
+    assert _rel(xv[:, :H * W].float(), want2) < 4e-3
+
+
+def test_gemm_segmented_matches_shifted_products():
+    """cmt_gemm_segmented: per-segment A column offset and row shift with zero fill outside the matrix, shared B per
+    group of batches (the task-head first convolution over the query axis, cmt_head.py:116-150)."""
+    g = torch.Generator().manual_seed(17)
+    nb, M, N, seg_k, a_cols = 4, 300, 96, 64, 192
+    guard = 2
+    A = torch.zeros(nb, M + 2 * guard, a_cols)
+    A[:, guard:guard + M] = torch.randn(nb, M, a_cols, generator=g)
+    A = A.bfloat16()
+    acol = [0, 64, 128, 0, 64]
+    shift = [-1, 0, 1, 2, -2]
+    Bm = (torch.randn(2, N, len(acol) * seg_k, generator=g) * 0.1).bfloat16()   # one weight set per 2 batches
+    bias = torch.randn(N, generator=g)
+    want = torch.zeros(nb, M, N, dtype=torch.float64)
+    Af = A.double()
+    for z in range(nb):
+        for s, (c, sh) in enumerate(zip(acol, shift)):
+            rows = Af[z, guard + sh:guard + sh + M, c:c + seg_k]
+            want[z] += rows @ Bm[z // 2, :, s * seg_k:(s + 1) * seg_k].double().T
+    want = want + bias.double()
+    C = torch.empty(nb, M, N, dtype=torch.float32, device=DEV)
+    ops.gemm_segmented(A.to(DEV), Bm.to(DEV), bias.to(DEV), C, M, N, seg_k, acol, shift, a_row_off=guard, a_rows=M + 2 * guard,
+                       a_cols=a_cols, lda=a_cols, ldb=len(acol) * seg_k, ldc=N, batch=nb, strideA=(M + 2 * guard) * a_cols,
+                       strideB=N * len(acol) * seg_k, b_batch_div=2, strideC=M * N)
+    torch.cuda.synchronize()
+    assert _rel(C, want) < 1e-5
+    # rows shifted past either end of the matrix read zeros (no guard rows at all, shift beyond the matrix)
+    A2 = torch.randn(1, M, a_cols, generator=g).bfloat16()
+    C2 = torch.empty(1, M, N, dtype=torch.float32, device=DEV)
+    ops.gemm_segmented(A2.to(DEV), Bm[:1].to(DEV), None, C2, M, N, seg_k, [0, 64], [-3, 5], a_row_off=0, a_rows=M,
+                       a_cols=a_cols, lda=a_cols, ldb=len(acol) * seg_k, ldc=N)
+    want2 = torch.zeros(M, N, dtype=torch.float64)
+    A2f = torch.zeros(M + 16, a_cols, dtype=torch.float64)
+    A2f[8:8 + M] = A2[0].double()
+    want2 += A2f[8 - 3:8 - 3 + M, 0:64] @ Bm[0, :, 0:64].double().T
+    want2 += A2f[8 + 5:8 + 5 + M, 64:128] @ Bm[0, :, 64:128].double().T
+    torch.cuda.synchronize()
+    assert _rel(C2[0], want2) < 1e-5
+
+
 def test_coop_max_and_lse_merge():
     a = torch.randn(3, 2, 50, 256)
     b = torch.randn(3, 2, 50, 256)
