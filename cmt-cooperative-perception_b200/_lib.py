@@ -26,7 +26,7 @@ SIGNATURES = {
     "cmt_check_device": (_i, [_i]),
     "cmt_ray_pe": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _i, _vp]),
     "cmt_ray_query_pe": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _i, _vp]),
-    "cmt_masked_view_sum": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cmt_masked_view_sum": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "cmt_pos2embed": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "cmt_gather_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cmt_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i,
@@ -41,7 +41,8 @@ SIGNATURES = {
     "cmt_lse_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cmt_coop_max": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "cmt_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "cmt_task_head_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cmt_task_head_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cmt_split3_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "cmt_debug_attn_timing": (_i, [_vp]),
 }
 

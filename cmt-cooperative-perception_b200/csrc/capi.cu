@@ -167,10 +167,10 @@ int cmt_ray_query_pe(const float* ref, const float* lidar2img, const float* img2
                                out_dtype, static_cast<cudaStream_t>(stream));
 }
 
-int cmt_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq, int C,
-                        int emb_dtype, void* stream) {
+int cmt_masked_view_sum(const void* emb, const float* mask, const float* base, int64_t base_bstride, float* out, int B, int V,
+                        int Nq, int C, int emb_dtype, void* stream) {
     CMT_REQUIRE_DEVICE();
-    return launch_masked_view_sum(emb, mask, out, B, V, Nq, C, emb_dtype, static_cast<cudaStream_t>(stream));
+    return launch_masked_view_sum(emb, mask, base, base_bstride, out, B, V, Nq, C, emb_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype, void* stream) {
@@ -373,10 +373,19 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
 }
 
 int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
-                       int L, int M, int NH, int HC, int CMAX, float eps, void* stream) {
+                       int L, int M, int NH, int HC, int CMAX, float eps, int ksize, int Nq, const float* ref_logit,
+                       const int* dec_comp, const float* dec_scale, const float* dec_offset, const int64_t* head_off_host,
+                       const int* head_cout_host, void* stream) {
     CMT_REQUIRE_DEVICE();
     CMT_CHECK_ARG(h && gamma && beta && w2 && b2 && out, "cmt_task_head_tail: null pointer");
-    return launch_task_head_tail(h, gamma, beta, w2, b2, out, L, M, NH, HC, CMAX, eps, static_cast<cudaStream_t>(stream));
+    return launch_task_head_tail(h, gamma, beta, w2, b2, out, L, M, NH, HC, CMAX, eps, ksize, Nq, ref_logit, dec_comp, dec_scale,
+                                 dec_offset, reinterpret_cast<const long long*>(head_off_host), head_cout_host,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_split3(a, b, out, merged, Z, Nq, C, static_cast<cudaStream_t>(stream));
 }
 
 int cmt_debug_attn_timing(void* dev_buf_i64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_i64)); }

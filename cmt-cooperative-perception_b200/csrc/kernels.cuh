@@ -53,8 +53,8 @@ int launch_ray_pe(const float* img2lidar, void* out, int n_cam, int H, int W, in
 int launch_ray_query_pe(const float* ref, const float* l2i, const float* i2l, void* out,
                         float* mask, int B, int V, int Nq, int D, float pad_h, float pad_w,
                         const float* pc, int out_dtype, cudaStream_t stream);
-int launch_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq,
-                           int C, int emb_dtype, cudaStream_t stream);
+int launch_masked_view_sum(const void* emb, const float* mask, const float* base, long long base_bstride, float* out, int B,
+                           int V, int Nq, int C, int emb_dtype, cudaStream_t stream);
 int launch_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int out_dtype,
                      cudaStream_t stream);
 // gather_kernels.cu
@@ -71,7 +71,10 @@ int launch_add_layernorm(const float* x, const float* r, const float* gamma, con
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
                          void* yadd, int lp_dtype, cudaStream_t stream);
 int launch_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
-                          int L, int M, int NH, int HC, int CMAX, float eps, cudaStream_t stream);
+                          int L, int M, int NH, int HC, int CMAX, float eps, int ksize, int Nq, const float* ref_logit,
+                          const int* dec_comp, const float* dec_scale, const float* dec_offset, const long long* head_off_host,
+                          const int* head_cout_host, cudaStream_t stream);
+int launch_split3(const float* a, const float* b, void* out, float* merged, long long Z, int Nq, int C, cudaStream_t stream);
 // simt_kernels.cu
 int launch_simt_gemm(const GemmArgs& g, int batch, int in_dtype, cudaStream_t stream);
 int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256) ray_query_pe_kernel(const float* __restri
 template <bool kBf16>
 __global__ void __launch_bounds__(256) masked_view_sum_kernel(const void* __restrict__ emb,
                                                               const float* __restrict__ mask,
+                                                              const float* __restrict__ base, long long base_bstride,
                                                               float* __restrict__ out, int B, int V,
                                                               int Nq, int C) {
     const long long total = static_cast<long long>(B) * Nq * C;
@@ -205,6 +206,8 @@ __global__ void __launch_bounds__(256) masked_view_sum_kernel(const void* __rest
                 e = reinterpret_cast<const float*>(emb)[row * C + c];
             acc += e * m;
         }
+        // query_embeds = bev_query_embeds + rv_query_embeds (cmt_head.py:492): the view sum first, then the BEV part
+        if (base != nullptr) acc = base[static_cast<long long>(b) * base_bstride + static_cast<long long>(n) * C + c] + acc;
         out[t] = acc;
     }
 }
@@ -306,16 +309,16 @@ int launch_ray_query_pe(const float* ref, const float* l2i, const float* i2l, vo
     return CMT_OK;
 }
 
-int launch_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq,
-                           int C, int emb_dtype, cudaStream_t stream) {
+int launch_masked_view_sum(const void* emb, const float* mask, const float* base, long long base_bstride, float* out, int B,
+                           int V, int Nq, int C, int emb_dtype, cudaStream_t stream) {
     CMT_CHECK_ARG(emb && mask && out, "cmt_masked_view_sum: null pointer");
     CMT_CHECK_ARG(B > 0 && V > 0 && Nq > 0 && C > 0, "cmt_masked_view_sum: bad shape");
     const long long total = static_cast<long long>(B) * Nq * C;
     const int grid = grid_for(total, 256);
     if (emb_dtype == CMT_BF16)
-        masked_view_sum_kernel<true><<<grid, 256, 0, stream>>>(emb, mask, out, B, V, Nq, C);
+        masked_view_sum_kernel<true><<<grid, 256, 0, stream>>>(emb, mask, base, base_bstride, out, B, V, Nq, C);
     else if (emb_dtype == CMT_F32)
-        masked_view_sum_kernel<false><<<grid, 256, 0, stream>>>(emb, mask, out, B, V, Nq, C);
+        masked_view_sum_kernel<false><<<grid, 256, 0, stream>>>(emb, mask, base, base_bstride, out, B, V, Nq, C);
     else
         CMT_CHECK_ARG(false, "cmt_masked_view_sum: bad dtype");
     CMT_LAUNCH_CHECK("cmt_masked_view_sum");

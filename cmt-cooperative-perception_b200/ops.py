@@ -133,15 +133,22 @@ def ray_query_pe(ref, lidar2img, img2lidar, depth_num, pad_h, pad_w, pc_range, o
     return out, mask
 
 
-def masked_view_sum(emb, mask):
-    """(emb * mask[..., None]).sum(1)  (cmt_head.py:466). emb [B,V,Nq,C] -> [B,Nq,C] fp32."""
+def masked_view_sum(emb, mask, base=None):
+    """base + (emb * mask[..., None]).sum(1)  (cmt_head.py:466, :492). emb [B,V,Nq,C] -> [B,Nq,C] fp32.
+    base: optional fp32 [B,Nq,C] or [Nq,C] (shared by every frame) added after the view sum."""
     emb = _cuda(emb, "emb")
     mask = _cuda(mask, "mask", torch.float32)
     B, V, Nq, C = emb.shape
     out = torch.empty((B, Nq, C), dtype=torch.float32, device=emb.device)
+    bstride = 0
+    if base is not None:
+        base = _cuda(base, "base", torch.float32)
+        assert base.shape in ((B, Nq, C), (Nq, C))
+        bstride = Nq * C if base.dim() == 3 else 0
     lib = _lib.load()
     with torch.cuda.device(emb.device):
-        rc = lib.cmt_masked_view_sum(_ptr(emb), _ptr(mask), _ptr(out), B, V, Nq, C, _dt(emb.dtype), _stream(emb))
+        rc = lib.cmt_masked_view_sum(_ptr(emb), _ptr(mask), _ptr(base), bstride, _ptr(out), B, V, Nq, C, _dt(emb.dtype),
+                                     _stream(emb))
     _lib.check(rc, "cmt_masked_view_sum")
     _count()
     return out
@@ -493,19 +500,64 @@ def add_layernorm(x, r, gamma, beta, eps=1e-5, *, gamma2=None, beta2=None, y2=No
     return y, y2, ylp, yadd
 
 
-def task_head_tail(h, gamma, beta, w2, b2, eps):
-    """ReLU(GroupLN(h) * gamma + beta) . w2 + b2 for every (layer, row, output head) in one launch (cmt_head.py:116-150,
-    :53-94).  h [L,M,NH,64] fp32; gamma/beta [L,NH,64]; w2 [L,NH,CMAX,64]; b2 [L,NH,CMAX] -> [L,M,NH,CMAX] fp32."""
+def split3(a, b=None, want_merged=False):
+    """Three-term bf16 split of the stacked decoder outputs with nan_to_num (and the cooperative max over two stacks)
+    fused in (cmt_split3_bf16).  a, b: [L,B,Nq,256] fp32 -> [L*B, Nq+2, 768] bf16 (, merged [L,B,Nq,256] fp32)."""
+    a = _cuda(a, "a", torch.float32)
+    L, B, Nq, C = a.shape
+    if b is not None:
+        b = _cuda(b, "b", torch.float32)
+        assert b.shape == a.shape
+    out = torch.empty((L * B, Nq + 2, 3 * C), dtype=torch.bfloat16, device=a.device)
+    merged = torch.empty_like(a) if want_merged else None
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.cmt_split3_bf16(_ptr(a), _ptr(b), _ptr(out), _ptr(merged), L * B, Nq, C, _stream(a))
+    _lib.check(rc, "cmt_split3_bf16")
+    _count()
+    return (out, merged) if want_merged else out
+
+
+def task_head_tail(h, gamma, beta, w2, b2, eps, ksize=1, Nq=None, ref_logit=None, dec_comp=None, dec_scale=None,
+                   dec_offset=None, head_couts=None):
+    """sum_t ReLU(GroupLN(h[q+t-k/2]) * gamma + beta) . w2[:, t] + b2 for every (layer, row, output head) in one launch,
+    plus the optional reference-point decode (cmt_head.py:116-150, :53-94, :501-513).  h [L,M,NH,64] fp32; gamma/beta
+    [L,NH,64]; w2 [L,NH,CMAX,ksize,64]; b2 [L,NH,CMAX] -> [L,M,NH,CMAX] fp32, or with head_couts=[c_0, ...] a list of
+    NH contiguous tensors [L,M,c_i] (views of one buffer: one device->host copy moves them all)."""
     h = _cuda(h, "h", torch.float32)
     L, M, NH, HC = h.shape
     CMAX = w2.shape[2]
+    if w2.dim() == 4:
+        w2 = w2.unsqueeze(3)
     args = [_cuda(t, n, torch.float32) for t, n in ((gamma, "gamma"), (beta, "beta"), (w2, "w2"), (b2, "b2"))]
     assert args[0].shape == (L, NH, HC) and args[1].shape == (L, NH, HC)
-    assert args[2].shape == (L, NH, CMAX, HC) and args[3].shape == (L, NH, CMAX)
-    out = torch.empty((L, M, NH, CMAX), dtype=torch.float32, device=h.device)
+    assert args[2].shape == (L, NH, CMAX, ksize, HC) and args[3].shape == (L, NH, CMAX)
+    Nq = M if Nq is None else Nq
+    if ref_logit is not None:
+        ref_logit = _cuda(ref_logit, "ref_logit", torch.float32)
+        assert ref_logit.shape == (M, 3)
+        dec_comp = _cuda(dec_comp, "dec_comp", torch.int32)
+        dec_scale = _cuda(dec_scale, "dec_scale", torch.float32)
+        dec_offset = _cuda(dec_offset, "dec_offset", torch.float32)
+        assert dec_comp.numel() == NH * CMAX and dec_scale.numel() == NH * CMAX and dec_offset.numel() == NH * CMAX
+    offs = couts = None
+    if head_couts is not None:
+        assert len(head_couts) == NH and NH <= 8
+        sizes = [L * M * int(c) for c in head_couts]
+        starts = [sum(sizes[:i]) for i in range(NH)]
+        out = torch.empty((sum(sizes),), dtype=torch.float32, device=h.device)
+        offs = (ctypes.c_int64 * NH)(*starts)
+        couts = (ctypes.c_int * NH)(*[int(c) for c in head_couts])
+    else:
+        out = torch.empty((L, M, NH, CMAX), dtype=torch.float32, device=h.device)
     lib = _lib.load()
     with torch.cuda.device(h.device):
-        rc = lib.cmt_task_head_tail(_ptr(h), *[_ptr(a) for a in args], _ptr(out), L, M, NH, HC, CMAX, float(eps), _stream(h))
+        rc = lib.cmt_task_head_tail(_ptr(h), *[_ptr(a) for a in args], _ptr(out), L, M, NH, HC, CMAX, float(eps), ksize, Nq,
+                                    _ptr(ref_logit), _ptr(dec_comp), _ptr(dec_scale), _ptr(dec_offset),
+                                    None if offs is None else ctypes.cast(offs, ctypes.c_void_p),
+                                    None if couts is None else ctypes.cast(couts, ctypes.c_void_p), _stream(h))
     _lib.check(rc, "cmt_task_head_tail")
     _count()
+    if head_couts is not None:
+        return [out[s:s + n].view(L, M, int(c)) for s, n, c in zip(starts, sizes, head_couts)]
     return out

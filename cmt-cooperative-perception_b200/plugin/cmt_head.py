@@ -98,55 +98,100 @@ class SeparateTaskHead(nn.Module):
             if head == "cls_logits":
                 getattr(self, head)[-1].bias.data.fill_(self.init_bias)
 
-    def _k1_weights(self):
-        """final_kernel == 1: the grouped 1x1 Conv1d pairs are per-decoder-layer GEMMs.  Stack the six heads:
-        W1 [L, H*64, C], LN affine [L, 1, H, 64], W2 [L, H, cmax, 64] (zero padded), b2 [L, 1, H, cmax]."""
+    # -- fused inference path: tensor-core first convolution (three-term bf16 split) + one tail kernel -----------------
+    _PAIRS = ((0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0))   # (term of x, term of w): every product down to 2^-24
+
+    def fusable(self, x):
+        """True when libcmtcoop_b200 computes this head: CUDA, eval, (conv, GroupLN, ReLU, conv) stacks with
+        head_conv = 64, kernel size 1 or 3, 256 input channels, at most 8 heads of at most 32 outputs."""
+        if self.training or not x.is_cuda or not self._two_stage or self._kernel_size not in (1, 3) or len(self.heads) > 8:
+            return False
+        seqs = [getattr(self, n) for n in self.heads]
+        return all(s[0].weight.shape[0] == 64 * self.groups and s[0].weight.shape[1] == 256 and
+                   s[3].weight.shape[0] // self.groups <= 32 for s in seqs) and x.shape[-1] == 256
+
+    def _fused_weights(self):
+        """Stacks the heads: first conv as a segmented-GEMM B operand [L, NH*64, KS*6*C] bf16 (weights split into three
+        bf16 terms, six products per tap), LN affine [L,NH,64], second conv [L,NH,cmax,KS,64] (zero padded), bias."""
         names = list(self.heads)
         seqs = [getattr(self, n) for n in names]
         key = tuple((s[0].weight._version, s[0].weight.data_ptr(), s[1].weight._version, s[1].bias._version,
                      s[3].weight._version, s[3].bias._version) for s in seqs)
-        hit = self.__dict__.get("_k1_cache")
+        hit = self.__dict__.get("_fused_cache")
         if hit is None or hit[0] != key:
-            L = self.groups
+            L, KS = self.groups, self._kernel_size
             hc = seqs[0][0].weight.shape[0] // L
             C = seqs[0][0].weight.shape[1]
+            NH = len(seqs)
             couts = [s[3].weight.shape[0] // L for s in seqs]
             cmax = max(couts)
-            w1 = torch.stack([s[0].weight.detach().view(L, hc, C) for s in seqs], 1).reshape(L, len(seqs) * hc, C)
-            g = torch.stack([s[1].weight.detach().view(L, hc) for s in seqs], 1).unsqueeze(1)
-            b = torch.stack([s[1].bias.detach().view(L, hc) for s in seqs], 1).unsqueeze(1)
-            w2 = w1.new_zeros(L, len(seqs), cmax, hc)
-            b2 = w1.new_zeros(L, 1, len(seqs), cmax)
+            w1 = torch.stack([s[0].weight.detach().float().view(L, hc, C, KS) for s in seqs], 1).reshape(L, NH * hc, C, KS)
+            t1 = w1.bfloat16()
+            r1 = w1 - t1.float()
+            t2 = r1.bfloat16()
+            t3 = (r1 - t2.float()).bfloat16()
+            terms = (t1, t2, t3)
+            segs, acol, shift = [], [], []
+            for t in range(KS):
+                for xi, wj in self._PAIRS:
+                    segs.append(terms[wj][..., t])
+                    acol.append(xi * C)
+                    shift.append(t - KS // 2)
+            bmat = torch.cat(segs, dim=-1).contiguous()                      # [L, NH*hc, KS*6*C]
+            g = torch.stack([s[1].weight.detach().float().view(L, hc) for s in seqs], 1).contiguous()
+            b = torch.stack([s[1].bias.detach().float().view(L, hc) for s in seqs], 1).contiguous()
+            w2 = w1.new_zeros(L, NH, cmax, KS, hc)
+            b2 = w1.new_zeros(L, NH, cmax)
             for i, (s, co) in enumerate(zip(seqs, couts)):
-                w2[:, i, :co] = s[3].weight.detach().view(L, co, hc)
-                b2[:, 0, i, :co] = s[3].bias.detach().view(L, co)
-            hit = (key, (names, couts, hc, w1.transpose(1, 2).contiguous(), g, b, w2, b2, seqs[0][1].eps))
-            self.__dict__["_k1_cache"] = hit
+                w2[:, i, :co] = s[3].weight.detach().float().view(L, co, hc, KS).permute(0, 1, 3, 2)
+                b2[:, i, :co] = s[3].bias.detach().float().view(L, co)
+            hit = (key, dict(names=names, couts=couts, hc=hc, C=C, KS=KS, bmat=bmat, acol=acol, shift=shift, g=g, b=b,
+                             w2=w2.contiguous(), b2=b2.contiguous(), eps=seqs[0][1].eps, cmax=cmax))
+            self.__dict__["_fused_cache"] = hit
         return hit[1]
 
-    def _forward_k1(self, x):
-        """Same arithmetic as the Conv1d(k=1, groups=L) -> GroupLayerNorm1d -> ReLU -> Conv1d(k=1, groups=L)
-        stacks (cmt_head.py:116-150), as 1 bmm + 1 fused LN + 1 einsum for all six outputs instead of
-        ~250 cuDNN launches."""
-        L, B, Q, C = x.shape
-        names, couts, hc, w1t, g, b, w2, b2, eps = self._k1_weights()
-        h = torch.bmm(x.reshape(L, B * Q, C), w1t).view(L, B * Q, len(names), hc)
-        if x.is_cuda and hc == 64 and w2.shape[2] <= 32:
-            # group-LN + ReLU + second conv of all six outputs in one launch (fp32, libcmtcoop_b200)
-            out = ops.task_head_tail(h.contiguous(), g.reshape(L, len(names), hc).contiguous(),
-                                     b.reshape(L, len(names), hc).contiguous(), w2.contiguous(),
-                                     b2.reshape(L, len(names), -1).contiguous(), eps)
-            return {n: out[:, :, i, :co].reshape(L, B, Q, co) for i, (n, co) in enumerate(zip(names, couts))}
-        mu = h.mean(-1, keepdim=True)
-        var = (h - mu).pow(2).mean(-1, keepdim=True)
-        y = torch.relu((h - mu) / (var + eps).sqrt() * g + b)
-        out = torch.einsum("lmhc,lhoc->lmho", y, w2) + b2
-        return {n: out[:, :, i, :co].reshape(L, B, Q, co) for i, (n, co) in enumerate(zip(names, couts))}
+    def _decode_tables(self, pc_range, device):
+        """Per (head, output) reference component / scale / offset of the reference-point decode (cmt_head.py:501-513)."""
+        w = self._fused_weights()
+        key = (tuple(float(v) for v in pc_range), str(device))
+        hit = self.__dict__.get("_dec_cache")
+        if hit is None or hit[0] != key:
+            NH, cmax = len(w["names"]), w["cmax"]
+            comp = torch.full((NH, cmax), -1, dtype=torch.int32)
+            scale = torch.ones(NH, cmax)
+            off = torch.zeros(NH, cmax)
+            pc = [float(v) for v in pc_range]
+            for i, n in enumerate(w["names"]):
+                if n == "center":
+                    for o in range(2):
+                        comp[i, o], scale[i, o], off[i, o] = o, pc[3 + o] - pc[o], pc[o]
+                elif n == "height":
+                    comp[i, 0], scale[i, 0], off[i, 0] = 2, pc[5] - pc[2], pc[2]
+            hit = (key, (comp.to(device), scale.to(device), off.to(device)))
+            self.__dict__["_dec_cache"] = hit
+        return hit[1]
+
+    def forward_split(self, xs, B, Q, ref_logit=None, pc_range=None):
+        """xs: ops.split3 of the decoder outputs, [L*B, Q+2, 768] bf16.  Returns {name: [L,B,Q,c_out]} fp32 -- with
+        ref_logit [B*Q,3] the center / height outputs are already decoded to metric coordinates."""
+        w = self._fused_weights()
+        L, C, KS, hc = self.groups, w["C"], w["KS"], w["hc"]
+        NH = len(w["names"])
+        h = torch.empty((L, B * Q, NH, hc), dtype=torch.float32, device=xs.device)
+        ops.gemm_segmented(xs, w["bmat"], None, h, Q, NH * hc, C, w["acol"], w["shift"], a_row_off=1, a_rows=Q + 2,
+                           a_cols=3 * C, lda=3 * C, ldb=KS * 6 * C, ldc=NH * hc, batch=L * B, strideA=(Q + 2) * 3 * C,
+                           strideB=NH * hc * KS * 6 * C, b_batch_div=B, strideC=Q * NH * hc, tag="task_head_conv1")
+        dec = (None, None, None)
+        if ref_logit is not None:
+            dec = self._decode_tables(pc_range, xs.device)
+        outs = ops.task_head_tail(h, w["g"], w["b"], w["w2"], w["b2"], w["eps"], ksize=KS, Nq=Q, ref_logit=ref_logit,
+                                  dec_comp=dec[0], dec_scale=dec[1], dec_offset=dec[2], head_couts=w["couts"])
+        return {n: o.view(L, B, Q, co) for n, o, co in zip(w["names"], outs, w["couts"])}
 
     def forward(self, x):
         N, B, Q, C = x.shape
-        if self._kernel_size == 1 and self._two_stage and not self.training:
-            return self._forward_k1(x)
+        if self.fusable(x):
+            return self.forward_split(ops.split3(x.contiguous().float()), B, Q)   # note: applies nan_to_num like the head does
         x = x.permute(1, 0, 3, 2).reshape(B, N * C, Q)  # "n b q c -> b (n c) q"
         ret = {}
         for head in self.heads:
@@ -280,7 +325,26 @@ class _CmtHeadBase(nn.Module):
     def prepare_for_dn(self, batch_size, reference_points, img_metas):
         if self.training:
             raise NotImplementedError("denoising queries are training-only (cmt_head.py:339-408)")
-        return reference_points.unsqueeze(0).repeat(batch_size, 1, 1), None, None
+        # eval branch (cmt_head.py:410-413): the learned reference points repeated over the batch -- a function of the
+        # parameter only, so the repeated tensor (and everything derived from it alone) is cached per parameter version
+        return self._ref_derived(batch_size, reference_points)["ref"], None, None
+
+    def _ref_derived(self, batch_size, reference_points):
+        """Tensors that depend on the reference points (and weights) only, cached per parameter version and batch size:
+        ref [B,Nq,3]; ref_clamped = inverse_sigmoid(ref).sigmoid() (cmt_head.py:470); ref_logit = inverse_sigmoid(ref)
+        [B*Nq,3] (:501); bev_query = bev_embedding(pos2embed(ref_clamped)) [Nq,C] (:435-437, identical for every frame)."""
+        key = (reference_points.data_ptr(), reference_points._version, batch_size, str(reference_points.device), self.precision,
+               id(self._mlp_weights("bev_embedding")[0]) if reference_points.is_cuda else None)
+        hit = self._cache.get("ref")
+        if hit is None or hit[0] != key:
+            ref = reference_points.detach().unsqueeze(0).repeat(batch_size, 1, 1)
+            d = dict(ref=ref, ref_logit=inverse_sigmoid(ref.clone()).reshape(-1, 3).contiguous(),
+                     ref_clamped=inverse_sigmoid(ref.clone()).sigmoid())
+            if ref.is_cuda:
+                d["bev_query"] = self._bev_query_embed(d["ref_clamped"][:1], None)[0].contiguous()
+            hit = (key, d)
+            self._cache["ref"] = hit
+        return hit[1]
 
     # -- MLPs on the tcgen05 GEMM ---------------------------------------------------------
     def _mlp_weights(self, name):
@@ -376,8 +440,8 @@ class _CmtHeadBase(nn.Module):
         dt = _compute_dtype(self.precision)
         return self._mlp("bev_embedding", pos2embed(ref_points, num_pos_feats=self.hidden_dim, out_dtype=dt))
 
-    def _rv_query_embed(self, ref_points, img_metas, mats=None):
-        """cmt_head.py:439-467."""
+    def _rv_query_embed(self, ref_points, img_metas, mats=None, base=None):
+        """cmt_head.py:439-467 (+ `base`, the BEV query embedding, added after the view sum: :492)."""
         pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
         if mats is None:
             mats = self._matrices(img_metas, ref_points.device)
@@ -385,16 +449,36 @@ class _CmtHeadBase(nn.Module):
         feats, mask = ops.ray_query_pe(ref_points.contiguous(), mats[0], mats[1], self.depth_num, pad_h, pad_w,
                                        self.pc_range, out_dtype=dt)
         emb = self._mlp("rv_embedding", feats)
-        return ops.masked_view_sum(emb, mask)
+        return ops.masked_view_sum(emb, mask, base=base)
 
     def query_embed(self, ref_points, img_metas, mats=None):
+        """cmt_head.py:469-473 -> (bev_query_embeds, rv_query_embeds)."""
         ref_points = inverse_sigmoid(ref_points.clone()).sigmoid()
         bev = self._bev_query_embed(ref_points, img_metas)
         rv = self._rv_query_embed(ref_points, img_metas, mats) if self._has_img else None
         return bev, rv
 
+    def _query_embeds(self, reference_points, img_metas, mats):
+        """bev + rv query embedding [B,Nq,C] (cmt_head.py:491-492) with the weight-only parts taken from the cache."""
+        B = reference_points.shape[0]
+        d = None
+        hit = self._cache.get("ref")
+        if hit is not None and hit[1]["ref"] is reference_points:
+            d = hit[1]
+        if d is None or "bev_query" not in d:   # reference points not from prepare_for_dn: the general path
+            bev, rv = self.query_embed(reference_points, img_metas, mats)
+            return bev if rv is None else bev + rv
+        if not self._has_img:
+            return d["bev_query"].unsqueeze(0).expand(B, -1, -1)
+        return self._rv_query_embed(d["ref_clamped"], img_metas, mats, base=d["bev_query"])
+
     # -- one node: shared_conv -> PEs -> transformer -> nan_to_num ---------------------------
     def get_outs_dec(self, x, x_img, img_metas, reference_points, attn_mask):
+        """cmt_head_coop.py:341-360 (== cmt_head.py:481-499): stacked decoder outputs of one node, nan_to_num'ed."""
+        return torch.nan_to_num(self._outs_dec_raw(x, x_img, img_metas, reference_points, attn_mask))
+
+    def _outs_dec_raw(self, x, x_img, img_metas, reference_points, attn_mask):
+        # without the nan_to_num: the fused task-head path applies it inside cmt_split3_bf16
         with _torch_math(self.precision):
             return self._get_outs_dec(x, x_img, img_metas, reference_points, attn_mask)
 
@@ -405,8 +489,7 @@ class _CmtHeadBase(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("CmtHead needs CUDA tensors: libcmtcoop_b200 has no CPU fallback")
         mats = self._matrices(img_metas, dev) if self._has_img else None
-        bev_q, rv_q = self.query_embed(reference_points, img_metas, mats)
-        query_embeds = bev_q if rv_q is None else bev_q + rv_q
+        query_embeds = self._query_embeds(reference_points, img_metas, mats)
         if self._has_bev and self._has_img:
             x = self._apply_shared_conv_to(x)
             rv_pos = self._rv_pe(x_img, img_metas, mats)
@@ -419,11 +502,27 @@ class _CmtHeadBase(nn.Module):
         else:
             rv_pos = self._rv_pe(x_img, img_metas, mats)
             outs_dec, _ = self.transformer(x_img, query_embeds, rv_pos, attn_masks=attn_mask, bs=len(img_metas))
-        return torch.nan_to_num(outs_dec)
+        return outs_dec
 
     # -- task heads + reference-point decode (cmt_head.py:501-547, eval branch) ---------------
-    def _finish(self, outs_dec, reference_points):
-        # the task heads feed the top-k: always strict fp32 (no TF32), they cost ~0.1 GF
+    def _finish(self, outs_dec, reference_points, outs_dec_other=None):
+        """outs_dec: raw stacked decoder outputs [L,B,Nq,C] (nan_to_num not yet applied); outs_dec_other: the second node's
+        stack for the cooperative heads -- merged with the element-wise max (cmt_head_coop.py:383-389)."""
+        if all(t.fusable(outs_dec) for t in self.task_heads):
+            # libcmtcoop_b200: nan_to_num (+ V2I max) + three-term split -> tensor-core first conv -> fused tail with the
+            # reference-point decode; fp32-grade arithmetic (the logits feed the top-k)
+            L, B, Q, C = outs_dec.shape
+            xs = ops.split3(outs_dec.contiguous(), None if outs_dec_other is None else outs_dec_other.contiguous())
+            hit = self._cache.get("ref")
+            if hit is not None and hit[1]["ref"] is reference_points:
+                ref_logit = hit[1]["ref_logit"]
+            else:
+                ref_logit = inverse_sigmoid(reference_points.clone()).reshape(-1, 3).contiguous()
+            return [t.forward_split(xs, B, Q, ref_logit, self.pc_range) for t in self.task_heads]
+        outs_dec = torch.nan_to_num(outs_dec)
+        if outs_dec_other is not None:
+            outs_dec = ops.coop_max(outs_dec.contiguous(), torch.nan_to_num(outs_dec_other).contiguous())
+        # torch path (non-standard head shapes): strict fp32 (no TF32), these outputs feed the top-k
         with _torch_math("fp32"):
             return self._finish_impl(outs_dec, reference_points)
 
@@ -466,7 +565,7 @@ class CmtHead(_CmtHeadBase):
     def forward_single(self, x, x_img, img_metas):
         reference_points = self.reference_points.weight
         reference_points, attn_mask, mask_dict = self.prepare_for_dn(x.shape[0], reference_points, img_metas)
-        outs_dec = self.get_outs_dec(x, x_img, img_metas, reference_points, attn_mask)
+        outs_dec = self._outs_dec_raw(x, x_img, img_metas, reference_points, attn_mask)
         return self._finish(outs_dec, reference_points)
 
     def forward(self, pts_feats, img_feats=None, img_metas=None):
@@ -483,7 +582,7 @@ class CmtImageHead(CmtHead):
         assert x is None
         reference_points = self.reference_points.weight
         reference_points, attn_mask, mask_dict = self.prepare_for_dn(len(img_metas), reference_points, img_metas)
-        outs_dec = self.get_outs_dec(None, x_img, img_metas, reference_points, attn_mask)
+        outs_dec = self._outs_dec_raw(None, x_img, img_metas, reference_points, attn_mask)
         return self._finish(outs_dec, reference_points)
 
 
@@ -496,5 +595,5 @@ class CmtLidarHead(CmtHead):
         assert x_img is None
         reference_points = self.reference_points.weight
         reference_points, attn_mask, mask_dict = self.prepare_for_dn(x.shape[0], reference_points, img_metas)
-        outs_dec = self.get_outs_dec(x, None, img_metas, reference_points, attn_mask)
+        outs_dec = self._outs_dec_raw(x, None, img_metas, reference_points, attn_mask)
         return self._finish(outs_dec, reference_points)

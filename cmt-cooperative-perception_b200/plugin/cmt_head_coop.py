@@ -49,12 +49,15 @@ class CmtHeadCoop(_CmtHeadBase):
         reference_points, attn_mask, mask_dict = self.prepare_for_dn(len(img_metas), reference_points, img_metas)
         out_v = out_i = None
         if x_vehicle is not None or x_img_vehicle is not None:
-            out_v = self.get_outs_dec(x_vehicle, x_img_vehicle, get_vehicle_image_metas(img_metas),
-                                      reference_points, attn_mask)
+            out_v = self._outs_dec_raw(x_vehicle, x_img_vehicle, get_vehicle_image_metas(img_metas),
+                                       reference_points, attn_mask)
         if x_infrastructure is not None or x_img_infrastructure is not None:
-            out_i = self.get_outs_dec(x_infrastructure, x_img_infrastructure,
-                                      get_infrastructure_image_metas(img_metas), reference_points, attn_mask)
-        return self._finish(self._merge(out_v, out_i), reference_points)
+            out_i = self._outs_dec_raw(x_infrastructure, x_img_infrastructure,
+                                       get_infrastructure_image_metas(img_metas), reference_points, attn_mask)
+        if out_v is None or out_i is None:
+            return self._finish(out_v if out_i is None else out_i, reference_points)
+        # max(stack([veh, infra]), 0) (cmt_head_coop.py:383-389) is folded into the task heads' first kernel
+        return self._finish(out_v, reference_points, outs_dec_other=out_i)
 
     def forward(self, vehicle_pts_feats, infrastructure_pts_feats, vehicle_img_feats=None,
                 infrastructure_img_feats=None, img_metas=None):

@@ -62,9 +62,11 @@ int cmt_ray_query_pe(const float* ref, const float* lidar2img, const float* img2
                      float* mask, int B, int V, int Nq, int D, float pad_h, float pad_w,
                      const float* pc_range_host, int out_dtype, void* stream);
 
-/* out[b,n,:] = sum_v mask[b,v,n] * emb[b,v,n,:]  (cmt_head.py:466). emb fp32|bf16, out fp32. */
-int cmt_masked_view_sum(const void* emb, const float* mask, float* out, int B, int V, int Nq,
-                        int C, int emb_dtype, void* stream);
+/* out[b,n,:] = base[b,n,:] + sum_v mask[b,v,n] * emb[b,v,n,:]  (cmt_head.py:466 and the `bev + rv` of :492).
+ * emb fp32|bf16, out fp32; base (nullable) fp32 at base + b*base_bstride + n*C (base_bstride = 0: one [Nq,C]
+ * embedding shared by every frame -- in eval the BEV query embedding depends on the weights only). */
+int cmt_masked_view_sum(const void* emb, const float* mask, const float* base, int64_t base_bstride, float* out,
+                        int B, int V, int Nq, int C, int emb_dtype, void* stream);
 
 /* ---- sine/cosine BEV embedding ------------------------------------------------------
  * pos2embed (cmt_head.py:40-50) including its `dim_t = 2*(i//2)/F + 1` divisor.
@@ -192,17 +194,34 @@ int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const 
                       int M, int C, float* y, const float* gamma2, const float* beta2, float* y2,
                       const float* add, void* ylp, void* yadd, int lp_dtype, void* stream);
 
-/* ---- task heads: group-LN + ReLU + second 1x1 conv --------------------------------------
- * The tail of SeparateTaskHead (models/dense_heads/cmt_head.py:116-150 with GroupLayerNorm1d :53-94,
- * final_kernel = 1) after the first grouped 1x1 conv, for all output heads at once:
- *   h:     [L, M, NH, HC] fp32   first-conv output, L = decoder layers (conv groups), M = B*Nq rows,
+/* ---- task heads -------------------------------------------------------------------------
+ * SeparateTaskHead (models/dense_heads/cmt_head.py:97-203 with GroupLayerNorm1d :53-94) for all output heads at once,
+ * final_kernel k = 1 (fusion / camera configs) or 3 (LiDAR configs: the convolutions run over the QUERY axis), fp32-grade
+ * arithmetic throughout (these logits feed the top-k, multi_task_bbox_coder.py:61-64).  Three launches:
+ *
+ * 1. cmt_split3_bf16: a (and optionally b) [Z, Nq, 256] fp32 -> out bf16 [Z, Nq + 2, 768] = [x1 | x2 | x3] per row with
+ *    x = nan_to_num(a) (cmt_head.py:499), or max(nan_to_num(a), nan_to_num(b)) for the cooperative heads
+ *    (cmt_head_coop.py:358,383-389), x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2); rows 0 and Nq + 1 of every
+ *    z are zero (convolution padding).  Z = decoder layers * frames.  `merged` (nullable): fp32 copy of x, [Z, Nq, 256].
+ * 2. cmt_gemm_segmented with 6 segments per tap (x1w1, x1w2, x2w1, x1w3, x2w2, x3w1; the weights split the same way):
+ *    the first grouped convolution as a tensor-core GEMM that reproduces the fp32 product to ~2^-22.
+ * 3. cmt_task_head_tail: group-LN + ReLU + second convolution (+ optional reference-point decode):
+ *   h:     [L, M, NH, HC] fp32   first-conv output, L = decoder layers (conv groups), M = frames*Nq rows,
  *                                NH = output heads (center, height, dim, rot, vel, cls_logits), HC = 64
  *   gamma, beta: [L, NH, HC]     GroupLayerNorm1d affine;  eps: its epsilon (1e-6)
- *   w2:    [L, NH, CMAX, HC], b2: [L, NH, CMAX]   second conv, zero-padded to CMAX <= 32 outputs per head
- *   out:   [L, M, NH, CMAX] fp32 = ReLU(LN(h) * gamma + beta) . w2 + b2 */
+ *   w2:    [L, NH, CMAX, ksize, HC], b2: [L, NH, CMAX]   second conv, zero-padded to CMAX <= 32 outputs per head
+ *   out:   [L, M, NH, CMAX] fp32 = sum_t ReLU(LN(h[q + t - ksize/2]) * gamma + beta) . w2[:, t] + b2
+ *          (rows outside a frame's [0, Nq) contribute zero: Conv1d zero padding of the hidden activations)
+ *   ref_logit (nullable): [M, 3] fp32 inverse_sigmoid(reference points); with it, output (head, o) whose
+ *          dec_comp[head*CMAX + o] = c >= 0 becomes sigmoid(out + ref_logit[row][c]) * dec_scale[..] + dec_offset[..]
+ *          (cmt_head.py:501-513: center and height to metric coordinates); dec_* are DEVICE arrays of NH*CMAX entries.
+ *   head_off_host / head_cout_host (nullable HOST arrays of NH entries, NH <= 8): instead of the padded layout, head i is
+ *          written as its own contiguous [L, M, cout[i]] tensor starting at out + off[i] (elements). */
+int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, void* stream);
 int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2,
                        const float* b2, float* out, int L, int M, int NH, int HC, int CMAX, float eps,
-                       void* stream);
+                       int ksize, int Nq, const float* ref_logit, const int* dec_comp, const float* dec_scale,
+                       const float* dec_offset, const int64_t* head_off_host, const int* head_cout_host, void* stream);
 
 /* ---- cooperative V2I merge ----------------------------------------------------------
  * out = max(nan_to_num(a), nan_to_num(b)) element-wise (cmt_head_coop.py:358,383-389). */

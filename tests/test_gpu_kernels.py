@@ -441,20 +441,87 @@ def test_cross_attention_static_shift(masked):
     assert (lse - lse0).abs().max() < 6e-3
 
 
-def test_task_head_tail():
-    """cmt_task_head_tail against the eager GroupLayerNorm1d / ReLU / 1x1 conv arithmetic (cmt_head.py:53-94, 116-150)."""
+@pytest.mark.parametrize("ks", [1, 3])
+def test_task_head_tail(ks):
+    """cmt_task_head_tail against the eager GroupLayerNorm1d / ReLU / Conv1d(k) arithmetic (cmt_head.py:53-94, 116-150),
+    k = 3 mixing neighbouring queries with zero padding at the ends of every frame, plus the reference-point decode
+    (cmt_head.py:501-513) and the per-head contiguous output form."""
+    import torch.nn.functional as F
     g = torch.Generator().manual_seed(4)
-    L, M, NH, HC, CMAX = 6, 1801, 6, 64, 10
+    L, Bf, Nq, NH, HC, CMAX = 6, 2, 901, 6, 64, 10
+    M = Bf * Nq
     h = torch.randn(L, M, NH, HC, generator=g) * 3 + 0.5
     gamma, beta = torch.randn(L, NH, HC, generator=g), torch.randn(L, NH, HC, generator=g)
-    w2, b2 = torch.randn(L, NH, CMAX, HC, generator=g) * 0.2, torch.randn(L, NH, CMAX, generator=g)
+    w2, b2 = torch.randn(L, NH, CMAX, ks, HC, generator=g) * 0.2, torch.randn(L, NH, CMAX, generator=g)
     eps = 1e-6
     hd = h.double()
     mu = hd.mean(-1, keepdim=True)
     var = (hd - mu).pow(2).mean(-1, keepdim=True)
-    y = torch.relu((hd - mu) / (var + eps).sqrt() * gamma.double()[:, None] + beta.double()[:, None])
-    want = torch.einsum("lmhc,lhoc->lmho", y, w2.double()) + b2.double()[:, None]
+    y = torch.relu((hd - mu) / (var + eps).sqrt() * gamma.double()[:, None] + beta.double()[:, None])   # [L,M,NH,HC]
+    # Conv1d over the query axis of every frame: [L*NH groups] x [Bf] x [HC, Nq]
+    yc = y.view(L, Bf, Nq, NH, HC).permute(1, 0, 3, 4, 2).reshape(Bf, L * NH * HC, Nq)
+    wc = w2.double().permute(0, 1, 2, 4, 3).reshape(L * NH * CMAX, HC, ks)
+    want = F.conv1d(yc, wc, b2.double().reshape(-1), padding=ks // 2, groups=L * NH)                   # [Bf, L*NH*CMAX, Nq]
+    want = want.view(Bf, L, NH, CMAX, Nq).permute(1, 0, 4, 2, 3).reshape(L, M, NH, CMAX)
     d = lambda t: t.to(DEV)
-    out = ops.task_head_tail(d(h), d(gamma), d(beta), d(w2), d(b2), eps)
+    out = ops.task_head_tail(d(h), d(gamma), d(beta), d(w2), d(b2), eps, ksize=ks, Nq=Nq)
     assert out.shape == (L, M, NH, CMAX)
-    assert torch.allclose(out.cpu().double(), want, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(out.cpu().double(), want, atol=5e-5, rtol=1e-5)
+    # decode of (head 0: outputs 0,1 -> ref x,y) and (head 1: output 0 -> ref z) + per-head contiguous outputs
+    ref_logit = torch.randn(M, 3, generator=g)
+    comp = torch.full((NH, CMAX), -1, dtype=torch.int32)
+    scale, off = torch.ones(NH, CMAX), torch.zeros(NH, CMAX)
+    comp[0, 0], comp[0, 1], comp[1, 0] = 0, 1, 2
+    scale[0, 0], scale[0, 1], scale[1, 0] = 108.0, 108.0, 8.0
+    off[0, 0], off[0, 1], off[1, 0] = -54.0, -54.0, -5.0
+    couts = [2, 1, 3, 2, 2, 10]
+    outs = ops.task_head_tail(d(h), d(gamma), d(beta), d(w2), d(b2), eps, ksize=ks, Nq=Nq, ref_logit=d(ref_logit), dec_comp=d(comp),
+                              dec_scale=d(scale), dec_offset=d(off), head_couts=couts)
+    assert [tuple(o.shape) for o in outs] == [(L, M, c) for c in couts] and all(o.is_contiguous() for o in outs)
+    wantd = want.clone()
+    wantd[:, :, 0, 0] = torch.sigmoid(want[:, :, 0, 0] + ref_logit[:, 0].double()) * 108.0 - 54.0
+    wantd[:, :, 0, 1] = torch.sigmoid(want[:, :, 0, 1] + ref_logit[:, 1].double()) * 108.0 - 54.0
+    wantd[:, :, 1, 0] = torch.sigmoid(want[:, :, 1, 0] + ref_logit[:, 2].double()) * 8.0 - 5.0
+    for i, (o, c) in enumerate(zip(outs, couts)):
+        assert torch.allclose(o.cpu().double(), wantd[:, :, i, :c], atol=1e-4, rtol=1e-5), i
+
+
+def test_split3_and_fp32_grade_first_conv():
+    """cmt_split3_bf16: the three bf16 terms sum back to the fp32 value (to 2^-24 relative), nan_to_num and the
+    cooperative max are applied, guard rows are zero; and the six-product segmented GEMM built on it reproduces an fp32
+    (fp64-checked) matrix product to ~1e-6 -- the task heads' first convolution (cmt_head.py:116-150)."""
+    g = torch.Generator().manual_seed(8)
+    L, Bf, Nq, C = 2, 2, 300, 256
+    a = torch.randn(L, Bf, Nq, C, generator=g) * 2
+    b = torch.randn(L, Bf, Nq, C, generator=g) * 2
+    a[0, 0, 0, 0], a[0, 0, 0, 1], a[0, 0, 0, 2] = float("nan"), float("inf"), float("-inf")
+    xs, merged = ops.split3(a.to(DEV), b.to(DEV), want_merged=True)
+    want = torch.maximum(torch.nan_to_num(a), torch.nan_to_num(b))
+    assert torch.equal(merged.cpu(), want)
+    xs_c = xs.cpu().float().view(L * Bf, Nq + 2, 3, C)
+    assert float(xs_c[:, 0].abs().max()) == 0.0 and float(xs_c[:, -1].abs().max()) == 0.0
+    back = xs_c[:, 1:-1].double().sum(2).view(L, Bf, Nq, C)
+    fin = want.abs() < 1e30
+    assert ((back - want.double()).abs()[fin] <= want.double().abs()[fin] * 2.0 ** -23 + 1e-30).all()
+    xs1 = ops.split3(a.to(DEV))
+    assert torch.equal(xs1.cpu().float().view(L * Bf, Nq + 2, 3, C)[:, 1:-1, 0], torch.nan_to_num(a).bfloat16().float().view(L * Bf, Nq, C))
+    # first conv, k = 1, through the plugin's own weight packing
+    from cmtcoop_b200.plugin import SeparateTaskHead
+    heads = dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2), cls_logits=(10, 2))
+    for ks in (1, 3):
+        th = SeparateTaskHead(256, heads, groups=L, head_conv=64, final_kernel=ks)
+        torch.manual_seed(ks)
+        th.init_weights()
+        for n in heads:
+            getattr(th, n)[1].weight.data.uniform_(0.5, 1.5)
+            getattr(th, n)[1].bias.data.normal_(0, 0.1)
+        sd = {"t." + k: v.detach().clone() for k, v in th.state_dict().items()}
+        th = th.to(DEV).eval()
+        x = torch.nan_to_num(a)
+        with torch.no_grad():
+            got = th(x.to(DEV))
+        want_h = O.separate_task_head(x.double(), {k: v.double() for k, v in sd.items()}, "t", list(heads), ks)
+        for n in heads:
+            assert _rel(got[n], want_h[n]) < 3e-6, (ks, n, _rel(got[n], want_h[n]))
+
+
