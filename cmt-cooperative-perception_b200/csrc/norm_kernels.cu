@@ -186,6 +186,9 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ a
         for (int i = 0; i < 4; ++i) {
             const float x0 = v[2 * i], x1 = v[2 * i + 1];
             t1[i] = pack_bf16x2(x0, x1);
+            // a finite fp32 above the largest bf16 (nan_to_num turns inf into 3.4e38) must not round to infinity
+            if ((t1[i] & 0x00007f80u) == 0x00007f80u) t1[i] = (t1[i] & 0xffff8000u) | 0x00007f7fu;
+            if ((t1[i] & 0x7f800000u) == 0x7f800000u) t1[i] = (t1[i] & 0x8000ffffu) | 0x7f7f0000u;
             const float r0 = x0 - __uint_as_float(t1[i] << 16), r1 = x1 - __uint_as_float(t1[i] & 0xffff0000u);
             t2[i] = pack_bf16x2(r0, r1);
             const float s0 = r0 - __uint_as_float(t2[i] << 16), s1 = r1 - __uint_as_float(t2[i] & 0xffff0000u);
