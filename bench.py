@@ -321,6 +321,7 @@ def main():
         static_frac = None
         if fused_decoder.last_norms is not None:
             qn2, kn2 = fused_decoder.last_norms
+            kn2 = torch.cat(list(kn2)) if isinstance(kn2, (list, tuple)) else kn2
             bound = torch.sqrt(qn2 * kn2.permute(1, 0, 2)) * 1.0079 + 1e-3
             static_frac = float((bound <= 60.0).float().mean().item())
 

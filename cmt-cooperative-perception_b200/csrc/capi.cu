@@ -383,9 +383,10 @@ int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, co
                                  static_cast<cudaStream_t>(stream));
 }
 
-int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, void* stream) {
+int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, int frames,
+                    int64_t layer_stride_rows, void* stream) {
     CMT_REQUIRE_DEVICE();
-    return launch_split3(a, b, out, merged, Z, Nq, C, static_cast<cudaStream_t>(stream));
+    return launch_split3(a, b, out, merged, Z, Nq, C, frames, layer_stride_rows, static_cast<cudaStream_t>(stream));
 }
 
 int cmt_debug_attn_timing(void* dev_buf_i64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_i64)); }

@@ -74,7 +74,8 @@ int launch_task_head_tail(const float* h, const float* gamma, const float* beta,
                           int L, int M, int NH, int HC, int CMAX, float eps, int ksize, int Nq, const float* ref_logit,
                           const int* dec_comp, const float* dec_scale, const float* dec_offset, const long long* head_off_host,
                           const int* head_cout_host, cudaStream_t stream);
-int launch_split3(const float* a, const float* b, void* out, float* merged, long long Z, int Nq, int C, cudaStream_t stream);
+int launch_split3(const float* a, const float* b, void* out, float* merged, long long Z, int Nq, int C, int frames,
+                  long long layer_stride_rows, cudaStream_t stream);
 // simt_kernels.cu
 int launch_simt_gemm(const GemmArgs& g, int batch, int in_dtype, cudaStream_t stream);
 int launch_simt_attn(const AttnArgs& a, int dtype, cudaStream_t stream);

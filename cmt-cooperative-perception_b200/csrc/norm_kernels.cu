@@ -147,7 +147,8 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
 }
 
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                     __nv_bfloat16* __restrict__ out, float* __restrict__ merged, long long Z, int Nq) {
+                                                     __nv_bfloat16* __restrict__ out, float* __restrict__ merged, long long Z, int Nq,
+                                                     int frames, long long layer_stride) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -163,7 +164,10 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ a
             dst[64 + lane] = zero;
             continue;
         }
-        const long long src = (z * Nq + q) * 256 + lane * 8;
+        // input row of (layer, frame) = (z / frames, z % frames): layers may be further apart than frames * Nq rows (two
+        // nodes' frames stacked in one decoder pass: a = first half of every layer, b = second half)
+        const long long src = ((z / frames) * layer_stride + (z % frames) * Nq + q) * 256 + lane * 8;
+        const long long dense = (z * Nq + q) * 256 + lane * 8;
         float v[8];
         {
             const float4 p0 = *reinterpret_cast<const float4*>(a + src), p1 = *reinterpret_cast<const float4*>(a + src + 4);
@@ -178,8 +182,8 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ a
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], nan_to_num_f(w[i]));
         }
         if (merged != nullptr) {
-            *reinterpret_cast<float4*>(merged + src) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(merged + src + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<float4*>(merged + dense) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(merged + dense + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         uint32_t t1[4], t2[4], t3[4];
 #pragma unroll
@@ -200,8 +204,14 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ a
     }
 }
 
-int launch_split3(const float* a, const float* b, void* out, float* merged, long long Z, int Nq, int C, cudaStream_t stream) {
+int launch_split3(const float* a, const float* b, void* out, float* merged, long long Z, int Nq, int C, int frames,
+                  long long layer_stride_rows, cudaStream_t stream) {
     CMT_CHECK_ARG(a && out && Z > 0 && Nq > 0, "cmt_split3_bf16: bad arguments");
+    if (frames <= 0) {   // dense input [Z, Nq, C]
+        frames = 1;
+        layer_stride_rows = Nq;
+    }
+    CMT_CHECK_ARG(Z % frames == 0 && layer_stride_rows >= static_cast<long long>(frames) * Nq, "cmt_split3_bf16: bad layer stride");
     CMT_CHECK_ARG(C == 256, "cmt_split3_bf16: embed dim 256 only (got %d)", C);
     CMT_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
                     reinterpret_cast<uintptr_t>(merged)) & 15) == 0, "cmt_split3_bf16: pointers must be 16-byte aligned");
@@ -209,7 +219,7 @@ int launch_split3(const float* a, const float* b, void* out, float* merged, long
     long long blocks = (rows + 7) / 8;
     const long long cap = static_cast<long long>(device_sm_count()) * 16;
     if (blocks > cap) blocks = cap;
-    launch_pdl(split3_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, a, b, reinterpret_cast<__nv_bfloat16*>(out), merged, Z, Nq);
+    launch_pdl(split3_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, a, b, reinterpret_cast<__nv_bfloat16*>(out), merged, Z, Nq, frames, layer_stride_rows);
     CMT_LAUNCH_CHECK("cmt_split3_bf16");
     return CMT_OK;
 }

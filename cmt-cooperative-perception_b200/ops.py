@@ -387,7 +387,7 @@ def _workspace(dev, nbytes):
 
 
 def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False,
-               key_keep=None, q_norm2=None, k_norm2=None, tag="cross_attn"):
+               key_keep=None, q_norm2=None, k_norm2=None, tag="cross_attn", out=None):
     """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
     vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq]).
     key_keep: optional [B,N_kv] bool/uint8, True = attend (the key_padding_mask of attention.py:76-90, whose
@@ -403,7 +403,11 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
     assert Hk == H and vt.shape[:4] == (B, L, H, HEAD_DIM)
     kv_end = N_kv if kv_end is None else kv_end
     o_dtype = o_dtype or q.dtype
-    o = torch.empty((B, Nq, HD), dtype=o_dtype, device=q.device)
+    if out is not None:   # caller-provided output rows (a slice of a larger [frames, Nq, H*32] buffer)
+        o = _cuda(out, "out", o_dtype)
+        assert o.shape == (B, Nq, HD)
+    else:
+        o = torch.empty((B, Nq, HD), dtype=o_dtype, device=q.device)
     lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if return_lse else None
     esz = q.element_size()
     kp = ctypes.c_void_p(k.data_ptr() + layer * H * N_kv * HEAD_DIM * esz)
@@ -500,19 +504,29 @@ def add_layernorm(x, r, gamma, beta, eps=1e-5, *, gamma2=None, beta2=None, y2=No
     return y, y2, ylp, yadd
 
 
-def split3(a, b=None, want_merged=False):
+def split3(a, b=None, want_merged=False, stacked_nodes=False):
     """Three-term bf16 split of the stacked decoder outputs with nan_to_num (and the cooperative max over two stacks)
-    fused in (cmt_split3_bf16).  a, b: [L,B,Nq,256] fp32 -> [L*B, Nq+2, 768] bf16 (, merged [L,B,Nq,256] fp32)."""
+    fused in (cmt_split3_bf16).  a, b: [L,B,Nq,256] fp32 -> [L*B, Nq+2, 768] bf16 (, merged [L,B,Nq,256] fp32).
+    stacked_nodes: `a` is [L,2B,Nq,256] holding the first node's frames then the second node's in every layer (one
+    decoder pass over both nodes); the max is taken between frame b and frame B + b."""
     a = _cuda(a, "a", torch.float32)
     L, B, Nq, C = a.shape
-    if b is not None:
+    frames, lstride = 0, 0
+    bptr = None
+    if stacked_nodes:
+        assert b is None and B % 2 == 0
+        B //= 2
+        frames, lstride = B, 2 * B * Nq
+        bptr = ctypes.c_void_p(a.data_ptr() + B * Nq * C * 4)
+    elif b is not None:
         b = _cuda(b, "b", torch.float32)
         assert b.shape == a.shape
+        bptr = _ptr(b)
     out = torch.empty((L * B, Nq + 2, 3 * C), dtype=torch.bfloat16, device=a.device)
-    merged = torch.empty_like(a) if want_merged else None
+    merged = torch.empty((L, B, Nq, C), dtype=torch.float32, device=a.device) if want_merged else None
     lib = _lib.load()
     with torch.cuda.device(a.device):
-        rc = lib.cmt_split3_bf16(_ptr(a), _ptr(b), _ptr(out), _ptr(merged), L * B, Nq, C, _stream(a))
+        rc = lib.cmt_split3_bf16(_ptr(a), bptr, _ptr(out), _ptr(merged), L * B, Nq, C, frames, lstride, _stream(a))
     _lib.check(rc, "cmt_split3_bf16")
     _count()
     return (out, merged) if want_merged else out

@@ -12,6 +12,8 @@ from .cmt_head import (CmtHead, CmtImageHead, CmtLidarHead, GroupLayerNorm1d, Se
                        multi_apply, pos2embed)
 from .cmt_head_coop import (CmtHeadCoop, CmtImageHeadCoop, CmtLidarHeadCoop, filter_img_metas,
                             get_infrastructure_image_metas, get_vehicle_image_metas)
+from .detector_glue import (attach_calibration, bbox3d2result, coop_simple_test, coop_simple_test_pts, device_calibration,
+                            simple_test, simple_test_pts)
 
 
 def build_head(cfg):

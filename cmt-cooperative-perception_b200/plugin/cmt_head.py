@@ -398,7 +398,15 @@ class _CmtHeadBase(nn.Module):
 
     # -- position encodings -----------------------------------------------------------------
     def _matrices(self, img_metas, device):
-        """Host float64 inverse -> fp32 -> device, as cmt_head.py:428-429,441-444. [B,V,4,4] each."""
+        """Host float64 inverse -> fp32 -> device, as cmt_head.py:428-429,441-444. [B,V,4,4] each.
+        A calibration already built on the device (plugin/detector_glue.device_calibration, stored in
+        img_metas[0]['calibration']) is used as it is."""
+        cal = img_metas[0].get("calibration")
+        if cal is not None:
+            l2i_d, i2l_d = cal
+            if l2i_d.device != torch.device(device) or l2i_d.shape[0] != len(img_metas):
+                raise ValueError("img_metas[0]['calibration'] must hold [B,V,4,4] tensors on the head's device")
+            return l2i_d, i2l_d
         l2i = np.stack([np.asarray(m["lidar2img"], dtype=np.float64) for m in img_metas])
         # calibration rarely changes between frames: the inverse + upload (a host sync inside the path, SURVEY 8(f)
         # rank 3) is done once per distinct set of matrices, keyed by their bytes
@@ -482,6 +490,23 @@ class _CmtHeadBase(nn.Module):
         with _torch_math(self.precision):
             return self._get_outs_dec(x, x_img, img_metas, reference_points, attn_mask)
 
+    def _node_cache(self, x, x_img, img_metas, reference_points):
+        """Everything of one node up to the decoder: (query_embeds [B,Nq,C], KVCache) -- position encodings, token gather /
+        shared_conv, all-layer K / V^T projection.  Used by the cooperative heads to decode both nodes in one pass."""
+        dev = (x if x is not None else x_img).device
+        if dev.type != "cuda":
+            raise RuntimeError("CmtHead needs CUDA tensors: libcmtcoop_b200 has no CPU fallback")
+        B = len(img_metas)
+        mats = self._matrices(img_metas, dev) if self._has_img else None
+        query_embeds = self._query_embeds(reference_points, img_metas, mats)
+        tr = self.transformer
+        bev_pos = self._bev_pos_embed(dev).contiguous() if self._has_bev else None
+        rv_pos = self._rv_pe(x_img, img_metas, mats).contiguous() if self._has_img else None
+        xb = self._apply_shared_conv_to(x).contiguous() if self._has_bev else None
+        V = (x_img.shape[0] // B) if self._has_img else 0
+        cache, _ = tr.build_kv_cache(xb, x_img.contiguous() if self._has_img else None, bev_pos, rv_pos, B, V)
+        return query_embeds, cache
+
     def _get_outs_dec(self, x, x_img, img_metas, reference_points, attn_mask):
         if self.training:
             raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")
@@ -505,14 +530,22 @@ class _CmtHeadBase(nn.Module):
         return outs_dec
 
     # -- task heads + reference-point decode (cmt_head.py:501-547, eval branch) ---------------
-    def _finish(self, outs_dec, reference_points, outs_dec_other=None):
+    def _finish(self, outs_dec, reference_points, outs_dec_other=None, stacked_nodes=False):
         """outs_dec: raw stacked decoder outputs [L,B,Nq,C] (nan_to_num not yet applied); outs_dec_other: the second node's
-        stack for the cooperative heads -- merged with the element-wise max (cmt_head_coop.py:383-389)."""
+        stack for the cooperative heads -- merged with the element-wise max (cmt_head_coop.py:383-389); stacked_nodes:
+        outs_dec is [L,2B,Nq,C] with the first node's frames then the second node's in every layer."""
+        if stacked_nodes and not all(t.fusable(outs_dec) for t in self.task_heads):
+            B2 = outs_dec.shape[1] // 2
+            outs_dec, outs_dec_other, stacked_nodes = outs_dec[:, :B2], outs_dec[:, B2:], False
         if all(t.fusable(outs_dec) for t in self.task_heads):
             # libcmtcoop_b200: nan_to_num (+ V2I max) + three-term split -> tensor-core first conv -> fused tail with the
             # reference-point decode; fp32-grade arithmetic (the logits feed the top-k)
             L, B, Q, C = outs_dec.shape
-            xs = ops.split3(outs_dec.contiguous(), None if outs_dec_other is None else outs_dec_other.contiguous())
+            if stacked_nodes:
+                B //= 2
+                xs = ops.split3(outs_dec.contiguous(), stacked_nodes=True)
+            else:
+                xs = ops.split3(outs_dec.contiguous(), None if outs_dec_other is None else outs_dec_other.contiguous())
             hit = self._cache.get("ref")
             if hit is not None and hit[1]["ref"] is reference_points:
                 ref_logit = hit[1]["ref_logit"]

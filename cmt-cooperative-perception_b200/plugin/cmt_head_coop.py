@@ -37,6 +37,8 @@ def get_vehicle_image_metas(img_metas):
 class CmtHeadCoop(_CmtHeadBase):
     """cmt_head_coop.py:72-444 (multimodal, vehicle + infrastructure)."""
 
+    batch_nodes = True   # decode both nodes' frames in one pass (False: two sequential decoder passes like the reference)
+
     def _merge(self, out_v, out_i):
         if out_v is None:
             return out_i
@@ -47,6 +49,23 @@ class CmtHeadCoop(_CmtHeadBase):
     def forward_single(self, x_vehicle, x_infrastructure, x_img_vehicle, x_img_infrastructure, img_metas):
         reference_points = self.reference_points.weight
         reference_points, attn_mask, mask_dict = self.prepare_for_dn(len(img_metas), reference_points, img_metas)
+        has_v = x_vehicle is not None or x_img_vehicle is not None
+        has_i = x_infrastructure is not None or x_img_infrastructure is not None
+        if (has_v and has_i and attn_mask is None and self.batch_nodes and not self.training
+                and self.transformer.kv_split_group is None):
+            # Both nodes in ONE decoder pass: the reference runs the same decoder (shared weights, same reference points)
+            # once per node (cmt_head_coop.py:368-389, :946-1017); frames are independent, so stacking the two nodes'
+            # frames changes no arithmetic -- every small op of the decoder runs once over 2B frames, the cross-attention
+            # is launched per node (their token counts differ), and the V2I max + nan_to_num ride in the task heads'
+            # first kernel.
+            from .cmt_head import _torch_math
+            with _torch_math(self.precision):
+                q_v, c_v = self._node_cache(x_vehicle, x_img_vehicle, get_vehicle_image_metas(img_metas), reference_points)
+                q_i, c_i = self._node_cache(x_infrastructure, x_img_infrastructure, get_infrastructure_image_metas(img_metas),
+                                            reference_points)
+                outs = self.transformer.decode_nodes([c_v, c_i], torch.cat([q_v, q_i], 0))
+            if outs is not None:
+                return self._finish(outs, reference_points, stacked_nodes=True)
         out_v = out_i = None
         if x_vehicle is not None or x_img_vehicle is not None:
             out_v = self._outs_dec_raw(x_vehicle, x_img_vehicle, get_vehicle_image_metas(img_metas),

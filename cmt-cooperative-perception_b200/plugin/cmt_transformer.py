@@ -156,6 +156,13 @@ class _CmtTransformerBase(nn.Module):
         self.kv_split_group = group if group is not None else dist.group.WORLD
         return self
 
+    def decode_nodes(self, caches, query_embed, attn_masks=None):
+        """One decoder pass over several nodes' frames (query_embed [sum B_i, Nq, C], caches[i] covering B_i frames) when
+        the fused decoder supports the configuration; None otherwise (the caller then decodes node by node)."""
+        if self.training or not self.use_fused_decoder or not fused_decoder.supports(self.decoder, attn_masks, list(caches)):
+            return None
+        return fused_decoder.run(self.decoder, query_embed, list(caches), self.precision)
+
     def _decode(self, cache, query_embed, attn_masks, reg_branch):
         if self.training:
             raise NotImplementedError("libcmtcoop_b200 is forward/inference only (call .eval())")

@@ -25,7 +25,7 @@ from .attention import KVCache, _Q_SCALE, _compute_dtype
 
 _STD_ORDER = ("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")
 
-# diagnostics for bench.py: the operand-norm maxima of the last forward, (q_norm2 [L,B,H], k_norm2 [B,L,H]) or None.
+# diagnostics for bench.py: the operand-norm maxima of the last forward, (q_norm2 [L,B,H], [k_norm2 [B_i,L,H] per cache]) or None.
 # An attention item (layer, frame, head) takes the static-shift kernel iff sqrt(qn * kn) * 1.0079 + 1e-3 <= 60.
 last_norms = None
 
@@ -70,6 +70,9 @@ def _ln(norm: nn.LayerNorm):
 
 def supports(decoder, attn_masks, kv_cache) -> bool:
     """True when the fused path computes exactly what the generic module path would."""
+    if isinstance(kv_cache, (list, tuple)):
+        if not kv_cache or any(c is None or c.group is not None or c.k is None for c in kv_cache):
+            return False
     if kv_cache is None or decoder.training or not decoder.return_intermediate or decoder.post_norm is None:
         return False
     if attn_masks is not None and any(m is not None for m in (attn_masks if isinstance(attn_masks, (list, tuple))
@@ -90,8 +93,21 @@ def supports(decoder, attn_masks, kv_cache) -> bool:
     return True
 
 
-def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> torch.Tensor:
-    """query_pos [B,Nq,C] fp32 (batch-first).  Returns the stacked post-normed outputs [L,B,Nq,C] fp32."""
+def run(decoder, query_pos: torch.Tensor, cache, precision: str) -> torch.Tensor:
+    """query_pos [B,Nq,C] fp32 (batch-first).  Returns the stacked post-normed outputs [L,B,Nq,C] fp32.
+    cache: one KVCache for all B frames, or a list of KVCaches covering consecutive frame ranges (the cooperative heads:
+    both nodes' frames in ONE decoder pass -- shared weights and the same queries, cmt_head_coop.py:368-389 -- with one
+    cross-attention launch per node because the nodes' token counts differ; every small op runs once over 2B frames)."""
+    if isinstance(cache, (list, tuple)):
+        if len(cache) == 1:
+            cache = cache[0]
+        else:
+            return _run(decoder, query_pos, list(cache), precision)
+    return _run(decoder, query_pos, [cache], precision)
+
+
+def _run(decoder, query_pos, caches, precision):
+    cache = caches[0]
     dt = _compute_dtype(precision)
     B, Nq, C = query_pos.shape
     L = len(decoder.layers)
@@ -107,11 +123,11 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
 
     # max |q|^2 per (layer, frame, head) of the cross-attention queries: with cache.k_norm2 the attention kernel gets a
     # bound on every score and drops the running row maximum (ops.cross_attn)
-    static_shift = cache.k_norm2 is not None and dt == torch.bfloat16
+    static_shift = all(c.k_norm2 is not None for c in caches) and dt == torch.bfloat16
     qn2 = torch.zeros((L, B, H), dtype=torch.float32, device=dev) if static_shift else None
 
     global last_norms
-    last_norms = (qn2, cache.k_norm2) if static_shift else None
+    last_norms = (qn2, [c.k_norm2 for c in caches]) if static_shift else None   # k_norm2 per cache, frames in order
     for li, layer in enumerate(decoder.layers):
         # ---- self-attention over the queries: q = k = x + query_pos, v = x (key_pos = query_pos) ----
         sw = _mha_weights(layer.attentions[0].attn, dt)
@@ -127,16 +143,22 @@ def run(decoder, query_pos: torch.Tensor, cache: KVCache, precision: str) -> tor
         cw = mha.compute_weights()
         if static_shift:
             qc = ops.project_queries(x1q_lp, cw["wq"], cw["bq"], H, _Q_SCALE, norm2_max=qn2[li])
-            if cache.group is None:
-                ctx = ops.cross_attn(qc, cache.k, cache.vt, li, q_norm2=qn2[li], k_norm2=cache.k_norm2)
-            else:
-                ctx = mha._merge_kv_split(qc, cache, li, q_norm2=qn2[li])
-        elif cache.group is None:
-            qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
-            ctx = ops.cross_attn(qc, cache.k, cache.vt, li)
         else:
             qc = ops.linear(x1q_lp, cw["wq"], cw["bq"], alpha=_Q_SCALE, out_dtype=dt)
-            ctx = mha._merge_kv_split(qc, cache, li)
+        if len(caches) > 1:
+            ctx = torch.empty((B, Nq, C), dtype=dt, device=dev)
+            f0 = 0
+            for c in caches:
+                nb = c.k.shape[0]
+                ops.cross_attn(qc[f0:f0 + nb], c.k, c.vt, li, out=ctx[f0:f0 + nb],
+                               q_norm2=qn2[li][f0:f0 + nb] if static_shift else None, k_norm2=c.k_norm2 if static_shift else None)
+                f0 += nb
+            assert f0 == B
+        elif cache.group is None:
+            ctx = ops.cross_attn(qc, cache.k, cache.vt, li, q_norm2=qn2[li] if static_shift else None,
+                                 k_norm2=cache.k_norm2 if static_shift else None)
+        else:
+            ctx = mha._merge_kv_split(qc, cache, li, q_norm2=qn2[li] if static_shift else None)
         ca = ops.linear(ctx, cw["wo"], cw["bo"], out_dtype=torch.float32)
         g, b, eps = _ln(layer.norms[1])
         x2, _, x2_lp, _ = ops.add_layernorm(x1, ca, g, b, eps, lp_dtype=dt, want_ylp=True)

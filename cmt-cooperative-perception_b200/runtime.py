@@ -184,6 +184,8 @@ def _metas_key(img_metas):
                 out.append((k, np.asarray(m[k], dtype=np.float64).tobytes()))
             elif k.endswith("pad_shape"):
                 out.append((k, repr(m[k])))
+            elif k.endswith("calibration") and m[k] is not None:   # device tensors: the graph follows in-place updates
+                out.append((k, tuple(int(t.data_ptr()) for t in m[k])))
     return tuple(out)
 
 

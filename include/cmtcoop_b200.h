@@ -203,6 +203,9 @@ int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const 
  *    x = nan_to_num(a) (cmt_head.py:499), or max(nan_to_num(a), nan_to_num(b)) for the cooperative heads
  *    (cmt_head_coop.py:358,383-389), x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2); rows 0 and Nq + 1 of every
  *    z are zero (convolution padding).  Z = decoder layers * frames.  `merged` (nullable): fp32 copy of x, [Z, Nq, 256].
+ *    frames > 0: the inputs are strided -- row q of z = (layer, frame) sits at row layer*layer_stride_rows + frame*Nq + q
+ *    (both nodes' frames stacked in one decoder pass: a = the stack, b = a + frames*Nq*256, layer_stride_rows =
+ *    2*frames*Nq); frames = 0: dense [Z, Nq, 256].
  * 2. cmt_gemm_segmented with 6 segments per tap (x1w1, x1w2, x2w1, x1w3, x2w2, x3w1; the weights split the same way):
  *    the first grouped convolution as a tensor-core GEMM that reproduces the fp32 product to ~2^-22.
  * 3. cmt_task_head_tail: group-LN + ReLU + second convolution (+ optional reference-point decode):
@@ -217,7 +220,8 @@ int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const 
  *          (cmt_head.py:501-513: center and height to metric coordinates); dec_* are DEVICE arrays of NH*CMAX entries.
  *   head_off_host / head_cout_host (nullable HOST arrays of NH entries, NH <= 8): instead of the padded layout, head i is
  *          written as its own contiguous [L, M, cout[i]] tensor starting at out + off[i] (elements). */
-int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, void* stream);
+int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, int64_t Z, int Nq, int C, int frames,
+                    int64_t layer_stride_rows, void* stream);
 int cmt_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2,
                        const float* b2, float* out, int L, int M, int NH, int HC, int CMAX, float eps,
                        int ksize, int Nq, const float* ref_logit, const int* dec_comp, const float* dec_scale,

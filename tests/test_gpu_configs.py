@@ -187,3 +187,88 @@ def test_pipelined_runner_returns_every_batch():
     for a, b in zip(r16, r32):
         for n in NAMES:
             assert torch.equal(a[0][n], b[0][n])
+
+
+def test_detector_glue_and_device_calibration():
+    """plugin.detector_glue: simple_test_pts / coop_simple_test_pts (detectors/cmt.py:221-231, cmt_coop.py:549-569) return
+    the reference's result dicts; the calibration built on the device in float64 -- including the vehicle->infrastructure
+    fold of transforms_3d_coop.py:213-222 -- gives the same head outputs as the host numpy path."""
+    from cmtcoop_b200 import plugin
+    # --- single node
+    kind = "CmtHead"
+    cfg, inputs = synth.mini_case(kind)
+    head = build_head(cfg)
+    synth.load_synth_weights(head, 0)
+    head = head.to(DEV).eval().set_precision("fp32")
+    x, xi = torch.from_numpy(inputs["pts_feats"]).to(DEV), torch.from_numpy(inputs["img_feats"]).to(DEV)
+    metas = inputs["img_metas"]
+    with torch.no_grad():
+        res = plugin.simple_test(head, [x], [xi], metas)
+        outs = head([x], [xi], metas)
+        boxes = head.get_bboxes(outs, metas)
+    assert len(res) == len(metas) and set(res[0]["pts_bbox"]) == {"boxes_3d", "scores_3d", "labels_3d"}
+    for r, (bb, sc, lb) in zip(res, boxes):
+        assert torch.equal(r["pts_bbox"]["boxes_3d"], bb.cpu()) and torch.equal(r["pts_bbox"]["scores_3d"], sc.cpu())
+        assert not r["pts_bbox"]["labels_3d"].is_cuda
+    # device calibration == numpy float64 inverse (to fp32 rounding)
+    l2i = np.stack([np.asarray(m["lidar2img"], dtype=np.float64) for m in metas])
+    dl, di = plugin.device_calibration(l2i, DEV)
+    assert torch.equal(dl.cpu(), torch.from_numpy(l2i.astype(np.float32)))
+    want_inv = torch.from_numpy(np.linalg.inv(l2i).astype(np.float32))
+    assert ((di.cpu() - want_inv).abs() <= 2e-6 * want_inv.abs() + 1e-9).all()
+    import copy
+    metas2 = copy.deepcopy(metas)
+    plugin.attach_calibration(metas2, DEV)
+    with torch.no_grad():
+        a = head.forward_single(x, xi, metas)
+        b = head.forward_single(x, xi, metas2)
+    for n in NAMES:
+        assert O.rel_l2(b[0][n].cpu(), a[0][n].cpu()) < 1e-5, n
+    # --- cooperative: raw vehicle matrices + vehicle2infrastructure folded on the device
+    kind = "CmtHeadCoop"
+    cfg, inputs = synth.mini_case(kind)
+    head = build_head(cfg)
+    synth.load_synth_weights(head, 0)
+    head = head.to(DEV).eval().set_precision("fp32")
+    d = {k: (torch.from_numpy(v).to(DEV) if isinstance(v, np.ndarray) else v) for k, v in inputs.items()}
+    metas = inputs["img_metas"]
+    rng = np.random.RandomState(5)
+    raw = copy.deepcopy(metas)
+    for m in raw:   # un-fold: pretend the pipeline step was skipped; folded = raw @ inv(v2i)  =>  raw = folded @ v2i
+        v2i = synth.rigid_transform(rng)
+        m["vehicle2infrastructure"] = v2i
+        m["vehicle_lidar2img"] = [np.asarray(M) @ v2i for M in m["vehicle_lidar2img"]]
+    plugin.attach_calibration(raw, DEV, prefix="vehicle_", fold_vehicle2infrastructure=True)
+    plugin.attach_calibration(raw, DEV, prefix="infrastructure_")
+    args = (d["vehicle_pts_feats"], d["infrastructure_pts_feats"], d["vehicle_img_feats"], d["infrastructure_img_feats"])
+    with torch.no_grad():
+        a = head.forward_single(*args, metas)
+        b = head.forward_single(*args, raw)
+        res = plugin.coop_simple_test(head, *[[t] for t in args], metas)
+    for n in NAMES:
+        assert O.rel_l2(b[0][n].cpu(), a[0][n].cpu()) < 1e-4, n
+    assert len(res) == len(metas) and "pts_bbox" in res[0]
+
+
+@pytest.mark.parametrize("kind", ["CmtHeadCoop", "CmtLidarHeadCoop", "CmtImageHeadCoop"])
+def test_coop_node_batching_equals_sequential_passes(kind):
+    """The cooperative heads decode both nodes' frames in one pass (cmt_head_coop.py:368-389: same decoder, same queries,
+    frames independent): identical to two sequential decoder passes + cmt_coop_max up to bf16 batch-invariant rounding."""
+    cfg, inputs = synth.mini_case(kind)
+    head = build_head(cfg)
+    synth.load_synth_weights(head, 0)
+    head = head.to(DEV).eval().set_precision("bf16")
+    d = {k: (torch.from_numpy(v).to(DEV) if isinstance(v, np.ndarray) else v) for k, v in inputs.items()}
+    args = (d["vehicle_pts_feats"], d["infrastructure_pts_feats"], d["vehicle_img_feats"], d["infrastructure_img_feats"], d["img_metas"])
+    with torch.no_grad():
+        head.batch_nodes = True
+        n0 = ops.launch_count()
+        a = head.forward_single(*args)
+        n_batched = ops.launch_count() - n0
+        head.batch_nodes = False
+        n0 = ops.launch_count()
+        b = head.forward_single(*args)
+        n_seq = ops.launch_count() - n0
+    assert n_batched < n_seq
+    for n in NAMES:
+        assert O.rel_l2(a[0][n].float().cpu(), b[0][n].float().cpu()) < 1e-5, n   # per-frame arithmetic is identical
