@@ -8,6 +8,8 @@ is the cmt_coop_max kernel.
 """
 from __future__ import annotations
 
+import torch
+
 from .. import ops
 from .cmt_head import _CmtHeadBase, multi_apply
 from .registry import HEADS

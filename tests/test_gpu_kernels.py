@@ -519,6 +519,7 @@ def test_split3_and_fp32_grade_first_conv():
         sd = {"t." + k: v.detach().clone() for k, v in th.state_dict().items()}
         th = th.to(DEV).eval()
         x = torch.nan_to_num(a)
+        x[0, 0, 0, 1:3] = 0.0   # +-3.4e38 entries overflow the fp32 GroupLayerNorm statistics of the reference itself (NaN row)
         with torch.no_grad():
             got = th(x.to(DEV))
         want_h = O.separate_task_head(x.double(), {k: v.double() for k, v in sd.items()}, "t", list(heads), ks)
