@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the frame-0 oracle comparison (about 2 s of host work)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--kv-split-graph", action="store_true",
+                    help="with --kv-split: capture the forward INCLUDING the per-layer NCCL all-gathers in a CUDA graph")
     ap.add_argument("--no-shared-conv-leg", action="store_true", help="skip the second scope (step including shared_conv)")
     ap.add_argument("--kv-split", action="store_true",
                     help="BASELINE configs[4] variant: every rank sees the SAME frames and attends 1/N of the K/V tokens; "
@@ -255,8 +257,8 @@ def main():
     B = args.batch
     fdt = FEAT_DTYPES[args.feat_dtype]
     kv_split = args.kv_split and world > 1
-    if kv_split:
-        args.no_cuda_graph = True   # the per-layer NCCL all-gather stays outside graph capture
+    if kv_split and not args.kv_split_graph:
+        args.no_cuda_graph = True   # default: the per-layer NCCL all-gather stays outside graph capture
     kind, cfg, inputs = build_case(args.workload, B, seed=0 if kv_split else rank)
     head = build_head({k: v for k, v in cfg.items() if not k.startswith("_")})
     synth.load_synth_weights(head, 0)

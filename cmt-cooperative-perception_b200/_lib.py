@@ -28,7 +28,7 @@ SIGNATURES = {
     "cmt_ray_query_pe": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _i, _vp]),
     "cmt_masked_view_sum": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "cmt_pos2embed": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "cmt_gather_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "cmt_gather_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cmt_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i,
                                _i64, _i64, _i64, _f, _i, _i, _i, _vp, _vp]),
     "cmt_gemm_segmented": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i64, _i, _i64, _i64, _i64, _i, _i64, _i64, _i,
@@ -38,7 +38,7 @@ SIGNATURES = {
     "cmt_cross_attn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cmt_cross_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64,
                                 _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
-    "cmt_lse_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cmt_lse_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i, _vp]),
     "cmt_coop_max": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "cmt_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "cmt_task_head_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

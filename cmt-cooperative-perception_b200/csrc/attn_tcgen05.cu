@@ -73,12 +73,14 @@ struct TcAttnParams {
     int qblk;         // queries per item: 384 (three softmax warpgroups)
     int kt;           // KV tokens per tile-step: 128, or 64 for the double-buffered kernel
     int qblocks;      // ceil(Nq / qblk)
-    long long W;      // items * T
-    // Weighted stream-K: a step of an item whose last warpgroups are idle (the last query block of a frame/head
-    // when Nq is not a multiple of qblk) costs w_last instead of w_full; CTAs get equal WEIGHTED ranges.
-    int w_full, w_last;
-    long long Wg;     // weighted length of one (frame, head): T * (w_full * (qblocks - 1) + w_last)
-    long long Wtot;   // B * H * Wg
+    // Band-aligned stream-K.  Items are ordered query-block-major: item = qb * BH + hb (hb = b * H + h), so that "band" qb
+    // is the flat space BH x T of the K/V streams of every (frame, head).  Every full band is cut into n_full equal
+    // contiguous ranges, the last band (whose last warpgroups may be idle: cheaper steps) into n_last, one range per CTA:
+    // CTA c of band 0 and CTA c of band 1 then walk the SAME K/V tiles at the same time, so each tile comes from DRAM
+    // once and from L2 for the other bands (the (frame, head)-major order of round 1 streamed K/V from DRAM once per
+    // query block: 3.0x the algorithmic bytes).  n_full : n_last follows the measured step costs (w_full : w_last).
+    int BH;           // B * H
+    int n_full, n_last;
     int S_max;        // partial slots per item
     float* part_o;    // [items*S_max][qblk][32]
     float* part_lse;  // [items*S_max][qblk]   (log2 domain)
@@ -104,34 +106,23 @@ constexpr int TRACE_STEPS = 96;
 #define CMT_TRACE(wg_, step_, k_) do { } while (0)
 #endif
 
-// Weighted position of the start of global step x (x = item * T + step).
-__device__ __forceinline__ long long wpos_of(const TcAttnParams& p, long long x) {
-    const long long item = x / p.T;
-    const long long step = x - item * p.T;
-    const long long grp = item / p.qblocks;
-    const int qb = static_cast<int>(item - grp * p.qblocks);
-    return grp * p.Wg + static_cast<long long>(qb) * p.T * p.w_full + step * (qb == p.qblocks - 1 ? p.w_last : p.w_full);
-}
-// First global step of CTA c: the smallest x whose weighted position is >= c * Wtot / G.
+// First global step (x = item * T + step) of CTA c; c == G gives the end of the space.
 __device__ __forceinline__ long long range_start(const TcAttnParams& p, long long c, long long G) {
-    const long long t = (c * p.Wtot) / G;
-    const long long grp = t / p.Wg;
-    const long long rem = t - grp * p.Wg;
-    const long long full_span = static_cast<long long>(p.qblocks - 1) * p.T * p.w_full;
-    long long qb, step;
-    if (rem < full_span) {
-        qb = rem / (static_cast<long long>(p.T) * p.w_full);
-        step = (rem - qb * p.T * p.w_full + p.w_full - 1) / p.w_full;
-    } else {
-        qb = p.qblocks - 1;
-        step = (rem - full_span + p.w_last - 1) / p.w_last;
+    const long long S = static_cast<long long>(p.BH) * p.T;
+    const long long full_ctas = static_cast<long long>(p.qblocks - 1) * p.n_full;
+    if (c >= G) return p.qblocks * S;
+    if (c < full_ctas) {
+        const long long band = c / p.n_full, local = c - band * p.n_full;
+        return band * S + (local * S) / p.n_full;
     }
-    return (grp * p.qblocks + qb) * p.T + step;   // step == T carries into the next item
+    return static_cast<long long>(p.qblocks - 1) * S + ((c - full_ctas) * S) / p.n_last;
 }
 // The CTA whose range contains global step x.
-__device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long long G) {
-    const long long w = wpos_of(p, x);
-    return static_cast<int>(((w + 1) * G + p.Wtot - 1) / p.Wtot - 1);
+__device__ __forceinline__ int cta_of(const TcAttnParams& p, long long x, long long /*G*/) {
+    const long long S = static_cast<long long>(p.BH) * p.T;
+    const long long band = x / S, off = x - band * S;
+    const long long n = band < p.qblocks - 1 ? p.n_full : p.n_last;
+    return static_cast<int>(band * p.n_full + ((off + 1) * n - 1) / S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +157,17 @@ __global__ void pack_key_mask_kernel(const unsigned char* keep, unsigned long lo
 namespace attndb {
 #ifndef CMT_ATTN_NWG
 #define CMT_ATTN_NWG 3
+#endif
+// CMT_ATTN_PIPE=1: software-pipelined static softmax loop (half a score tile exponentiated while the other half's TMEM load
+// is in flight).  Measured in-step (B=8, 56 400 tokens): 880 us per launch against 824 us for the plain loop -- the wait
+// instructions between the halves split the 32-pair region the compiler otherwise interleaves freely (MUFU, FMA-pipe
+// polynomial and conversion work of both halves), and that instruction-level parallelism is worth more than the hidden
+// tcgen05.ld round trip.  Kept off, for the record.
+#ifndef CMT_ATTN_PIPE
+#define CMT_ATTN_PIPE 0
+#endif
+#ifndef CMT_ATTN_NACC
+#define CMT_ATTN_NACC 1     // independent row-sum accumulators per thread (breaks the 32-long dependent FADD2 chain)
 #endif
 constexpr int NWG = CMT_ATTN_NWG;
 constexpr int QBLK = NWG * 128;
@@ -220,6 +222,24 @@ constexpr int DB_POLY = CMT_ATTN_DB_POLY;
 #endif
 constexpr int ST_POLY = CMT_ATTN_ST_POLY;
 constexpr float STATIC_LIMIT = 60.0f;
+// pair i of a 16-pair chunk is polynomial when i % period == period - 1 (period 0: none)
+constexpr uint32_t poly_mask(int period) {
+    uint32_t m = 0;
+    for (int i = 0; i < 16; ++i)
+        if (period > 0 && i % period == period - 1) m |= 1u << i;
+    return m;
+}
+// explicit masks override the periods: -DCMT_ATTN_ST_MASK=0x5555 puts every other pair on the FMA pipes
+#ifdef CMT_ATTN_ST_MASK
+constexpr uint32_t ST_MASK = CMT_ATTN_ST_MASK;
+#else
+constexpr uint32_t ST_MASK = poly_mask(ST_POLY);
+#endif
+#ifdef CMT_ATTN_DB_MASK
+constexpr uint32_t DB_MASK = CMT_ATTN_DB_MASK;
+#else
+constexpr uint32_t DB_MASK = poly_mask(DB_POLY);
+#endif
 #ifndef CMT_ATTN_LONE_POLY
 #define CMT_ATTN_LONE_POLY 2
 #endif
@@ -299,7 +319,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     // MMA operands went through) decides.  Every role evaluates the same predicate, so skipped segments touch no barrier.
     auto mine = [&](int item) -> bool {
         if (p.q_norm2 == nullptr) return !kStatic;
-        const int hb = item / p.qblocks;   // b * H + h
+        const int hb = item % p.BH;   // b * H + h
         const float bound = sqrtf(__ldg(p.q_norm2 + hb) * __ldg(p.k_norm2 + static_cast<long long>(hb / p.H) * p.kn_bstride + hb % p.H)) * 1.0079f + 1e-3f;
         return (bound <= STATIC_LIMIT) == kStatic;
     };
@@ -314,9 +334,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
             if (!mine(item)) { pos += n; skipped = 1; continue; }
-            const int qb = item % p.qblocks;
-            const int h = (item / p.qblocks) % p.H;
-            const int b = item / (p.qblocks * p.H);
+            const int qb = item / p.BH;
+            const int h = (item % p.BH) % p.H;
+            const int b = (item % p.BH) / p.H;
             int nact = (p.Nq - qb * QBLK + 127) >> 7;
             nact = nact > NWG ? NWG : nact;
             mbar_wait_sleep(q_empty, (seg & 1) ^ 1);
@@ -368,7 +388,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
             if (!mine(item)) { pos += n; continue; }
-            const int qb = item % p.qblocks;
+            const int qb = item / p.BH;
             int nact = (p.Nq - qb * QBLK + 127) >> 7;   // warpgroups with queries; the others only release stages
             nact = nact > NWG ? NWG : nact;
             mbar_wait_sleep(q_full, seg & 1);
@@ -463,7 +483,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             const int item = static_cast<int>(pos / p.T);
             const int j0 = static_cast<int>(pos - static_cast<long long>(item) * p.T);
             const int n = static_cast<int>(min(static_cast<long long>(p.T - j0), pos_end - pos));
-            const int qb = item % p.qblocks;
+            const int qb = item / p.BH;
             pos += n;
             if (!mine(item)) continue;
             if (qb * QBLK + wg * 128 >= p.Nq) continue;     // this warpgroup's tile is past the last query
@@ -479,13 +499,15 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 pv_base += n - 1;
                 continue;
             }
-            const int hb = item / p.qblocks;                // b * H + h
+            const int hb = item % p.BH;                     // b * H + h
             const unsigned long long* mask_row = kMask ? p.mask_bits + static_cast<long long>(hb / p.H) * p.T : nullptr;
             float m = -INFINITY, l = 0.0f;
 
             // One KV step of this thread's row.
             auto step = [&](auto poly_tag, int jj) {
-                constexpr int POLY = decltype(poly_tag)::value;   // one pair of exponentials in POLY on the FMA pipes
+                // bit i of PMASK: pair i of each 16-pair chunk takes its two exponentials through the packed cubic on the
+                // FMA pipes instead of the MUFU
+                constexpr uint32_t PMASK = decltype(poly_tag)::value;
                 const uint32_t bsel = g & 1;
                 const uint32_t t_sb = t_s + bsel * 64;
                 CMT_S_WAIT(&my_s_full[bsel], (g >> 1) & 1);
@@ -554,7 +576,9 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                 // One PAIR of exponentials in POLY runs on the FMA pipes (packed cubic) instead of the MUFU; without
                 // the row-max work there are issue slots for more of them.
                 const uint64_t neg_m2 = pack_f32x2(-m, -m);
-                uint64_t l2 = pack_f32x2(0.f, 0.f);
+                uint64_t l2v[CMT_ATTN_NACC];
+#pragma unroll
+                for (int a = 0; a < CMT_ATTN_NACC; ++a) l2v[a] = pack_f32x2(0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t pk[16];
@@ -563,7 +587,7 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                         uint64_t x2 = pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
                         if (!kStatic) x2 = add_f32x2(x2, neg_m2);   // static: |s| <= 60, 2^s needs no shift at all
                         float e0, e1;
-                        if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+                        if ((PMASK >> i) & 1u) {
                             ex2_poly_pair<(!kStatic || kMask)>(x2, e0, e1);
                         } else {
                             float x0, x1;
@@ -571,12 +595,15 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                             e0 = ex2_approx(x0);
                             e1 = ex2_approx(x1);
                         }
-                        l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                        l2v[i % CMT_ATTN_NACC] = add_f32x2(l2v[i % CMT_ATTN_NACC], pack_f32x2(e0, e1));
                         pk[i] = pack_bf16x2(e0, e1);
                     }
                     tmem_st16(t_sb + c * 16, pk);
                 }
                 {
+                    uint64_t l2 = l2v[0];
+#pragma unroll
+                    for (int a = 1; a < CMT_ATTN_NACC; ++a) l2 = add_f32x2(l2, l2v[a]);
                     float l0, l1;
                     unpack_f32x2(l2, l0, l1);
                     l += l0 + l1;
@@ -597,10 +624,82 @@ tc_attn_db_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             // sub-partition (trace: 957 of 1165 cycles per step in the shared warp).  The lone warp therefore takes ALL
             // its exponentials through the polynomial on the otherwise idle FMA pipes and leaves the MUFU to its neighbour.
             const bool lone_warp = p.Nq - (qb * QBLK + wg * 128) <= 32;
+#if CMT_ATTN_PIPE
+            // Static-shift path, software-pipelined over the two 32-column halves of a score tile: the exponentials need no
+            // row statistic, so the first half can be exponentiated (and its P stored) while the TMEM load of the second
+            // half is in flight, and the first half of the NEXT step is loaded under the second half's exponentials.  A
+            // softmax warp then never sits on a tcgen05.ld round trip (three warps per scheduler cannot hide it).
+            auto run_static = [&](auto poly_tag) {
+                constexpr uint32_t PMASK = decltype(poly_tag)::value;
+                uint32_t s0[32], s1[32];
+                uint64_t l2 = pack_f32x2(0.f, 0.f);
+                auto half = [&](uint32_t (&sc)[32], uint32_t t_dst, int valid_c, uint32_t mbits) {
+                    if (kMask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (!((mbits >> i) & 1u)) sc[i] = 0xff800000u;
+                    } else if (valid_c < 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i >= valid_c) sc[i] = 0xc2fc0000u;   // -126: nothing next to weights >= 2^-60
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t x2 = pack_f32x2(__uint_as_float(sc[2 * i]), __uint_as_float(sc[2 * i + 1]));
+                        float e0, e1;
+                        if ((PMASK >> i) & 1u) {
+                            ex2_poly_pair<kMask>(x2, e0, e1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                        pk[i] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st16(t_dst, pk);
+                };
+                CMT_S_WAIT(&my_s_full[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                tmem_ld32(t_s + (g & 1) * 64, s0);
+                tc_wait_ld_regs(s0);
+                for (int jj = 0; jj < n; ++jj) {
+                    const uint32_t bsel = g & 1;
+                    const uint32_t t_sb = t_s + bsel * 64;
+                    tmem_ld32(t_sb + 32, s1);                       // second half in flight under the first half's work
+                    const int valid = p.kv_end - (p.kv_begin + (j0 + jj) * KT);
+                    unsigned long long mb = ~0ull;
+                    if (kMask) mb = __ldg(mask_row + j0 + jj);
+                    half(s0, t_sb, valid, static_cast<uint32_t>(mb));
+                    tc_wait_ld_regs(s1);
+                    if (jj + 1 < n) {                               // first half of the next step under the second half's work
+                        const uint32_t g1 = g + 1;
+                        CMT_S_WAIT(&my_s_full[g1 & 1], (g1 >> 1) & 1);
+                        tc_fence_after();
+                        tmem_ld32(t_s + (g1 & 1) * 64, s0);
+                    }
+                    half(s1, t_sb + 16, valid - 32, static_cast<uint32_t>(mb >> 32));
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&my_p_full[bsel]);
+                    ++g;
+                    if (jj + 1 < n) tc_wait_ld_regs(s0);
+                }
+                float l0, l1;
+                unpack_f32x2(l2, l0, l1);
+                l += l0 + l1;
+            };
+            if (kStatic) {
+                if (lone_warp) run_static(std::integral_constant<uint32_t, poly_mask(CMT_ATTN_LONE_POLY)>{});
+                else run_static(std::integral_constant<uint32_t, ST_MASK>{});
+            } else
+#endif
             if (lone_warp) {
-                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<int, CMT_ATTN_LONE_POLY>{}, jj);
+                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<uint32_t, poly_mask(CMT_ATTN_LONE_POLY)>{}, jj);
             } else {
-                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<int, (kStatic ? ST_POLY : DB_POLY)>{}, jj);
+                for (int jj = 0; jj < n; ++jj) step(std::integral_constant<uint32_t, (kStatic ? ST_MASK : DB_MASK)>{}, jj);
             }
             // segment epilogue: normalised partial + log2-sum-exp into the workspace
             mbar_wait(&o_full[wg], seg & 1);
@@ -646,7 +745,7 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
     const int item = blockIdx.x / chunks;
     const int rr = (blockIdx.x - item * chunks) * 32 + (threadIdx.x >> 3);
     const int q4 = threadIdx.x & 7;
-    const int qb = item % p.qblocks;
+    const int qb = item / p.BH;
     const int row = qb * QB + rr;
     if (qb * QB + (rr & ~31) >= p.Nq) return;         // the whole block is padding (block-uniform)
     if (threadIdx.x == 0) {
@@ -656,8 +755,8 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
     __syncthreads();
     if (row >= p.Nq) return;
     const int nseg = nseg_s;
-    const int h = (item / p.qblocks) % p.H;
-    const int b = item / (p.qblocks * p.H);
+    const int h = (item % p.BH) % p.H;
+    const int b = (item % p.BH) / p.H;
     float mx = -INFINITY;
     for (int s = 0; s < nseg; ++s)
         mx = fmaxf(mx, p.part_lse[(static_cast<long long>(item) * p.S_max + s) * QB + rr]);
@@ -697,13 +796,11 @@ __global__ void __launch_bounds__(256) tc_attn_merge_kernel(TcAttnParams p, long
 // (us per launch, B=8: static 842 @10:7 vs 858 @4:3; online 951 @4:3 vs 961 @10:7).
 static void attn_plan(int B, int H, int Nq, int n_tok, int sms, bool static_shift, TcAttnParams* p, int* grid,
                       long long* slots_out) {
-    const int per_cta = 1;
     p->qblk = attndb::QBLK;
     p->kt = attndb::KT;
     p->qblocks = (Nq + p->qblk - 1) / p->qblk;
     p->T = (n_tok + p->kt - 1) / p->kt;
-    const long long items = static_cast<long long>(B) * H * p->qblocks;
-    p->W = items * p->T;
+    p->BH = B * H;
     const int rows_last = Nq - (p->qblocks - 1) * p->qblk;
     // with every warpgroup active a step is MUFU-bound; with an idle warpgroup it is bound by one warpgroup's
     // own chain, ~3/4 of that
@@ -715,19 +812,28 @@ static void attn_plan(int B, int H, int Nq, int n_tok, int sms, bool static_shif
 #define CMT_ATTN_ON_WFULL 4
 #define CMT_ATTN_ON_WLAST 3
 #endif
-    p->w_full = static_shift ? CMT_ATTN_ST_WFULL : CMT_ATTN_ON_WFULL;
-    p->w_last = (rows_last + 127) / 128 < attndb::NWG ? (static_shift ? CMT_ATTN_ST_WLAST : CMT_ATTN_ON_WLAST) : p->w_full;
-    p->Wg = static_cast<long long>(p->T) * (static_cast<long long>(p->w_full) * (p->qblocks - 1) + p->w_last);
-    p->Wtot = static_cast<long long>(B) * H * p->Wg;
-    // no more slots than full-weight steps, so that a range is never shorter than the widest step
-    long long ctas = sms;
-    const long long max_ctas = p->Wtot / p->w_full / per_cta;
-    if (ctas > max_ctas) ctas = max_ctas;
-    if (ctas < 1) ctas = 1;
-    const long long G = ctas * per_cta;
-    long long chunk_min = p->Wtot / G;
-    if (chunk_min < 1) chunk_min = 1;
-    p->S_max = static_cast<int>((static_cast<long long>(p->T) * p->w_full - 1) / chunk_min + 2);
+    const long long w_full = static_shift ? CMT_ATTN_ST_WFULL : CMT_ATTN_ON_WFULL;
+    const long long w_last = (rows_last + 127) / 128 < attndb::NWG ? (static_shift ? CMT_ATTN_ST_WLAST : CMT_ATTN_ON_WLAST) : w_full;
+    const long long S = static_cast<long long>(p->BH) * p->T;   // steps of one band
+    const int nbf = p->qblocks - 1;                              // full bands
+    long long n_full = 0, n_last = sms;
+    if (nbf > 0) {
+        n_full = (sms * w_full + (w_full * nbf + w_last) / 2) / (w_full * nbf + w_last);   // CTAs per band ~ its share of the time
+        if (n_full * nbf > sms - 1) n_full = (sms - 1) / nbf;
+        if (n_full < 1) n_full = 1;
+        n_last = sms - n_full * nbf;
+        if (n_last < 1) n_last = 1;
+    }
+    if (n_full > S) n_full = S;   // no empty ranges
+    if (n_last > S) n_last = S;
+    p->n_full = static_cast<int>(n_full);
+    p->n_last = static_cast<int>(n_last);
+    const long long ctas = n_full * nbf + n_last;
+    const long long G = ctas;
+    long long len_min = S / n_last;
+    if (nbf > 0 && S / n_full < len_min) len_min = S / n_full;
+    if (len_min < 1) len_min = 1;
+    p->S_max = static_cast<int>((p->T - 1) / len_min + 2);
     *grid = static_cast<int>(ctas);
     *slots_out = G;
 }

@@ -180,10 +180,10 @@ int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int
 
 int cmt_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos, const float* rv_pos,
                       void* xk, void* xv, int B, int C, int n_bev, int V, int n_img, int tok_begin, int tok_end,
-                      int feat_dtype, int out_dtype, void* stream) {
+                      int rv_tok0, int rv_rows, int feat_dtype, int out_dtype, void* stream) {
     CMT_REQUIRE_DEVICE();
     return launch_gather_tokens(x_bev, x_img, bev_pos, rv_pos, xk, xv, B, C, n_bev, V, n_img, tok_begin, tok_end,
-                                feat_dtype, out_dtype, static_cast<cudaStream_t>(stream));
+                                rv_tok0, rv_rows, feat_dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int cmt_gemm_bias_act(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
@@ -392,9 +392,10 @@ int cmt_split3_bf16(const float* a, const float* b, void* out, float* merged, in
 int cmt_debug_attn_timing(void* dev_buf_i64) { return cmt::tc_attn_set_timing_buffer(static_cast<long long*>(dev_buf_i64)); }
 
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B, int H,
-                  int Nq, int o_dtype, void* stream) {
+                  int Nq, int64_t o_gstride, int64_t lse_gstride, int o_dtype, void* stream) {
     CMT_REQUIRE_DEVICE();
-    return launch_lse_merge(o_parts, lse_parts, o, lse, G, B, H, Nq, o_dtype, static_cast<cudaStream_t>(stream));
+    return launch_lse_merge(o_parts, lse_parts, o, lse, G, B, H, Nq, o_gstride, lse_gstride, o_dtype,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,

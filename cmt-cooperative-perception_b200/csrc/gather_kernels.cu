@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(
     const void* __restrict__ x_bev, const void* __restrict__ x_img,
     const float* __restrict__ bev_pos, const float* __restrict__ rv_pos, void* __restrict__ xk,
     void* __restrict__ xv, int C, int n_bev, int V, int n_img, int tiles_bev, int tiles_img, int tok_begin,
-    int tok_end) {
+    int tok_end, int rv_tok0, int rv_rows) {
     extern __shared__ float tile[];  // [kTileTok][C + 1]
     constexpr int ESZ = kIn == CMT_F32 ? 4 : 2;
     const int b = blockIdx.y;
@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(
         const int v = tix / tiles_img;
         const int cam = b * V + v;
         src = reinterpret_cast<const unsigned char*>(x_img) + static_cast<long long>(cam) * C * n_img * ESZ;
-        pos = rv_pos + static_cast<long long>(cam) * n_img * C;
+        // rv_pos holds rows [rv_tok0, rv_tok0 + rv_rows) of every frame's V * n_img image tokens (all of them by default; a
+        // rank of a KV-token split computes the position-encoding MLP for its own image tokens only)
+        pos = rv_pos + (static_cast<long long>(b) * rv_rows + static_cast<long long>(v) * n_img - rv_tok0) * C;
         n_src = n_img;
         t0 = (tix % tiles_img) * kTileTok;
         dst_tok0 = n_bev + static_cast<long long>(v) * n_img;
@@ -123,7 +125,8 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(
 
 int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                          const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                         int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, cudaStream_t stream) {
+                         int n_img, int tok_begin, int tok_end, int rv_tok0, int rv_rows, int feat_dtype, int out_dtype,
+                         cudaStream_t stream) {
     CMT_CHECK_ARG(xk && xv, "cmt_gather_tokens: null output");
     CMT_CHECK_ARG(B > 0 && C > 0 && (C % 2) == 0, "cmt_gather_tokens: bad B/C");
     CMT_CHECK_ARG(n_bev >= 0 && V >= 0 && n_img >= 0, "cmt_gather_tokens: bad token counts");
@@ -135,6 +138,17 @@ int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_
     const long long n_kv = n_bev + static_cast<long long>(V) * n_img;
     CMT_CHECK_ARG(0 <= tok_begin && tok_begin <= tok_end && tok_end <= n_kv, "cmt_gather_tokens: bad token range [%d,%d) of %lld",
                   tok_begin, tok_end, n_kv);
+    if (rv_rows <= 0) {   // default: rv_pos covers every image token
+        rv_tok0 = 0;
+        rv_rows = V * n_img;
+    }
+    {
+        // image tokens actually gathered must lie inside the rows rv_pos holds
+        const long long img_lo = tok_begin > n_bev ? tok_begin - n_bev : 0, img_hi = tok_end > n_bev ? tok_end - n_bev : 0;
+        CMT_CHECK_ARG(img_hi <= img_lo || (rv_tok0 <= img_lo && img_hi <= static_cast<long long>(rv_tok0) + rv_rows),
+                      "cmt_gather_tokens: rv_pos rows [%d, %d) do not cover the gathered image tokens [%lld, %lld)", rv_tok0,
+                      rv_tok0 + rv_rows, img_lo, img_hi);
+    }
     CMT_CHECK_ARG(feat_dtype == CMT_F32 || ((reinterpret_cast<uintptr_t>(x_bev) | reinterpret_cast<uintptr_t>(x_img)) & 3) == 0,
                   "cmt_gather_tokens: 16-bit feature maps must be 4-byte aligned");
     // x_bev == NULL with n_bev > 0: the BEV rows [0, n_bev) of xk / xv are produced elsewhere (the shared_conv epilogue,
@@ -148,7 +162,7 @@ int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_
     dim3 grid(tiles, B);
 #define CMT_GATHER_LAUNCH(OUT_BF16, IN)                                                                       \
     gather_tokens_kernel<OUT_BF16, IN><<<grid, 256, smem, stream>>>(x_bev, x_img, bev_pos, rv_pos, xk, xv, C, n_bev, V, \
-                                                                    n_img, tiles_bev, tiles_img, tok_begin, tok_end)
+                                                                    n_img, tiles_bev, tiles_img, tok_begin, tok_end, rv_tok0, rv_rows)
     const bool ob = out_dtype == CMT_BF16;
     if (feat_dtype == CMT_F32) { if (ob) CMT_GATHER_LAUNCH(true, CMT_F32); else CMT_GATHER_LAUNCH(false, CMT_F32); }
     else if (feat_dtype == CMT_BF16) { if (ob) CMT_GATHER_LAUNCH(true, CMT_BF16); else CMT_GATHER_LAUNCH(false, CMT_BF16); }
@@ -273,10 +287,8 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
                                                         const float* __restrict__ lse_parts,
                                                         void* __restrict__ o,
                                                         float* __restrict__ lse, int G, int B, int H,
-                                                        int Nq) {
+                                                        int Nq, long long part_o, long long part_l) {
     const long long total = static_cast<long long>(B) * Nq * H * 8;
-    const long long part_o = static_cast<long long>(B) * Nq * H * 32;
-    const long long part_l = static_cast<long long>(B) * H * Nq;
     for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int q4 = static_cast<int>(t & 7);
@@ -313,7 +325,10 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
 }
 
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
-                     int B, int H, int Nq, int o_dtype, cudaStream_t stream) {
+                     int B, int H, int Nq, long long o_gstride, long long lse_gstride, int o_dtype, cudaStream_t stream) {
+    if (o_gstride <= 0) o_gstride = static_cast<long long>(B) * Nq * H * 32;
+    if (lse_gstride <= 0) lse_gstride = static_cast<long long>(B) * H * Nq;
+    CMT_CHECK_ARG(o_gstride % 4 == 0 && (reinterpret_cast<uintptr_t>(o_parts) & 15) == 0, "cmt_lse_merge: o parts must be 16-byte aligned");
     CMT_CHECK_ARG(o_parts && lse_parts && o, "cmt_lse_merge: null pointer");
     CMT_CHECK_ARG(G > 0 && B > 0 && H > 0 && Nq > 0, "cmt_lse_merge: bad shape");
     const long long total = static_cast<long long>(B) * Nq * H * 8;
@@ -322,10 +337,10 @@ int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, floa
     if (blocks > cap) blocks = cap;
     if (o_dtype == CMT_BF16)
         lse_merge_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(o_parts, lse_parts, o,
-                                                                            lse, G, B, H, Nq);
+                                                                            lse, G, B, H, Nq, o_gstride, lse_gstride);
     else if (o_dtype == CMT_F32)
         lse_merge_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(o_parts, lse_parts, o,
-                                                                             lse, G, B, H, Nq);
+                                                                             lse, G, B, H, Nq, o_gstride, lse_gstride);
     else
         CMT_CHECK_ARG(false, "cmt_lse_merge: bad dtype");
     CMT_LAUNCH_CHECK("cmt_lse_merge");

@@ -60,12 +60,13 @@ int launch_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, 
 // gather_kernels.cu
 int launch_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                          const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                         int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, cudaStream_t stream);
+                         int n_img, int tok_begin, int tok_end, int rv_tok0, int rv_rows, int feat_dtype, int out_dtype,
+                         cudaStream_t stream);
 int launch_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, int W, int guard, int in_dtype,
                                cudaStream_t stream);
 int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
-                     int B, int H, int Nq, int o_dtype, cudaStream_t stream);
+                     int B, int H, int Nq, long long o_gstride, long long lse_gstride, int o_dtype, cudaStream_t stream);
 // norm_kernels.cu
 int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,

@@ -173,7 +173,7 @@ _FEAT_DTYPES = {torch.float32: CMT_F32, torch.bfloat16: CMT_BF16, torch.float16:
 
 
 def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16, tok_range=None, n_bev_reserved=0,
-                  out=None):
+                  out=None, rv_rows=None):
     """K4 (cmt_transformer.py:105-110 + petr_transformer.py:296-299).
     x_bev [B,C,Hb,Wb] | None, x_img [B*V,C,h,w] | None (fp32, bf16 or fp16 -- both the same dtype),
     bev_pos [N_bev,C], rv_pos [B*V*h*w, C] (any leading shape) fp32 -> xk = mem+pos, xv = mem, both
@@ -195,7 +195,8 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16,
         x_img = _cuda(x_img, "x_img", fdt)
         rv_pos = _cuda(rv_pos, "rv_pos", torch.float32)
         n_img = x_img.shape[2] * x_img.shape[3]
-        assert x_img.shape[0] == B * V and rv_pos.numel() == B * V * n_img * C
+        assert x_img.shape[0] == B * V
+        assert rv_pos.numel() == (B * V * n_img * C if rv_rows is None else B * (rv_rows[1] - rv_rows[0]) * C)
     else:
         V = 0
     if x_bev is None:
@@ -213,7 +214,9 @@ def gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=torch.bfloat16,
     lib = _lib.load()
     with torch.cuda.device(dev), _timed("gather_tokens", ref):
         rc = lib.cmt_gather_tokens(_ptr(x_bev), _ptr(x_img), _ptr(bev_pos), _ptr(rv_pos), _ptr(xk), _ptr(xv),
-                                   B, C, n_bev, V, n_img, lo, hi, _FEAT_DTYPES[fdt], _dt(out_dtype), _stream(ref))
+                                   B, C, n_bev, V, n_img, lo, hi, 0 if rv_rows is None else rv_rows[0],
+                                   0 if rv_rows is None else rv_rows[1] - rv_rows[0], _FEAT_DTYPES[fdt], _dt(out_dtype),
+                                   _stream(ref))
     _lib.check(rc, "cmt_gather_tokens")
     _count()
     return xk, xv
@@ -387,7 +390,7 @@ def _workspace(dev, nbytes):
 
 
 def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return_lse=False, simt=False,
-               key_keep=None, q_norm2=None, k_norm2=None, tag="cross_attn", out=None):
+               key_keep=None, q_norm2=None, k_norm2=None, tag="cross_attn", out=None, lse_out=None):
     """K3 (attention.py:46-92). q [B,Nq,H*32] pre-scaled by log2(e)/sqrt(32); k [B,L,H,N_kv,32];
     vt [B,L,H,32,ld]; attends tokens [kv_begin,kv_end) of layer `layer`. -> o [B,Nq,H*32] (, lse [B,H,Nq]).
     key_keep: optional [B,N_kv] bool/uint8, True = attend (the key_padding_mask of attention.py:76-90, whose
@@ -408,7 +411,12 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
         assert o.shape == (B, Nq, HD)
     else:
         o = torch.empty((B, Nq, HD), dtype=o_dtype, device=q.device)
-    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if return_lse else None
+    if lse_out is not None:
+        lse = _cuda(lse_out, "lse_out", torch.float32)
+        assert lse.shape == (B, H, Nq)
+        return_lse = True
+    else:
+        lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if return_lse else None
     esz = q.element_size()
     kp = ctypes.c_void_p(k.data_ptr() + layer * H * N_kv * HEAD_DIM * esz)
     vp = ctypes.c_void_p(vt.data_ptr() + layer * H * HEAD_DIM * ld * esz)
@@ -451,21 +459,44 @@ def cross_attn(q, k, vt, layer, *, kv_begin=0, kv_end=None, o_dtype=None, return
     return (o, lse) if return_lse else o
 
 
-def lse_merge(o_parts, lse_parts, o_dtype=torch.bfloat16):
+def lse_merge(o_parts, lse_parts, o_dtype=torch.bfloat16, want_lse=True):
     """Merge G partial attention results: o_parts [G,B,Nq,H*32] fp32, lse_parts [G,B,H,Nq] fp32."""
     o_parts = _cuda(o_parts, "o_parts", torch.float32)
     lse_parts = _cuda(lse_parts, "lse_parts", torch.float32)
     G, B, Nq, HD = o_parts.shape
     H = HD // HEAD_DIM
     o = torch.empty((B, Nq, HD), dtype=o_dtype, device=o_parts.device)
-    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=o_parts.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=o_parts.device) if want_lse else None
     lib = _lib.load()
     with torch.cuda.device(o_parts.device):
-        rc = lib.cmt_lse_merge(_ptr(o_parts), _ptr(lse_parts), _ptr(o), _ptr(lse), G, B, H, Nq, _dt(o_dtype),
+        rc = lib.cmt_lse_merge(_ptr(o_parts), _ptr(lse_parts), _ptr(o), _ptr(lse), G, B, H, Nq, 0, 0, _dt(o_dtype),
                                _stream(o_parts))
     _lib.check(rc, "cmt_lse_merge")
     _count()
     return o, lse
+
+
+def packed_partial(B, Nq, H, device):
+    """One (O | LSE) record: a flat fp32 buffer with views o [B,Nq,H*32] and lse [B,H,Nq] -- what a rank contributes to the
+    single all-gather of a KV-token-split decoder layer."""
+    n_o, n_l = B * Nq * H * HEAD_DIM, B * H * Nq
+    buf = torch.empty((n_o + n_l,), dtype=torch.float32, device=device)
+    return buf, buf[:n_o].view(B, Nq, H * HEAD_DIM), buf[n_o:].view(B, H, Nq)
+
+
+def lse_merge_packed(parts, G, B, Nq, H, o_dtype=torch.bfloat16):
+    """Merge the G packed (O | LSE) records of an all-gather: parts fp32 [G * (B*Nq*H*32 + B*H*Nq)] -> o [B,Nq,H*32]."""
+    parts = _cuda(parts, "parts", torch.float32)
+    n_o, n_l = B * Nq * H * HEAD_DIM, B * H * Nq
+    assert parts.numel() == G * (n_o + n_l)
+    o = torch.empty((B, Nq, H * HEAD_DIM), dtype=o_dtype, device=parts.device)
+    lib = _lib.load()
+    with torch.cuda.device(parts.device):
+        rc = lib.cmt_lse_merge(_ptr(parts), ctypes.c_void_p(parts.data_ptr() + n_o * 4), _ptr(o), None, G, B, H, Nq, n_o + n_l,
+                               n_o + n_l, _dt(o_dtype), _stream(parts))
+    _lib.check(rc, "cmt_lse_merge")
+    _count()
+    return o
 
 
 def coop_max(a, b):

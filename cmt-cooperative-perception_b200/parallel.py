@@ -44,6 +44,15 @@ def gather_partials(o_part: torch.Tensor, lse_part: torch.Tensor, group=None):
     return o_all.view((world,) + tuple(o_part.shape)), l_all.view((world,) + tuple(lse_part.shape))
 
 
+def gather_packed(record: torch.Tensor, group=None):
+    """All-gather of one packed (O | LSE) record per rank (ops.packed_partial): flat fp32 [n] -> [G * n].  ONE collective
+    per decoder layer is the whole data-path communication of the KV-token split."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * record.numel(),), dtype=record.dtype, device=record.device)
+    dist.all_gather_into_tensor(out, record, group=group)
+    return out
+
+
 def merge_partials_reference(o_all: torch.Tensor, l_all: torch.Tensor, num_heads: int):
     """Plain-torch statement of the LSE merge (what cmt_lse_merge computes); used by CPU tests."""
     G, B, Nq, C = o_all.shape

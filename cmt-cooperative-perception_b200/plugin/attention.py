@@ -182,14 +182,17 @@ class FlashMHA(nn.Module):
         """qp: already projected + pre-scaled queries [B,Nq,E]; q_norm2: optional [B,H] query norm maxima (with
         cache.k_norm2, the maxima over THIS rank's keys, they select the static-shift kernel for the local partial)."""
         from .. import parallel
+        import torch.distributed as dist
         B, Nq, E = qp.shape
-        q = qp
+        H = self.num_heads
+        # the local partial goes straight into the packed (O | LSE) record this rank contributes to the layer's all-gather
+        record, o_part, lse = ops.packed_partial(B, Nq, H, qp.device)
         if cache.n_kv > 0:
-            o_part, lse = ops.cross_attn(qp, cache.k, cache.vt, layer, return_lse=True, o_dtype=torch.float32,
-                                         q_norm2=q_norm2, k_norm2=cache.k_norm2 if q_norm2 is not None else None)
+            ops.cross_attn(qp, cache.k, cache.vt, layer, o_dtype=torch.float32, out=o_part, lse_out=lse,
+                           q_norm2=q_norm2, k_norm2=cache.k_norm2 if q_norm2 is not None else None)
         else:  # this rank holds no tokens: neutral element of the merge
-            o_part = torch.zeros((B, Nq, E), dtype=torch.float32, device=q.device)
-            lse = torch.full((B, self.num_heads, Nq), float("-inf"), dtype=torch.float32, device=q.device)
-        o_all, l_all = parallel.gather_partials(o_part, lse, cache.group)
-        ctx, _ = ops.lse_merge(o_all, l_all, o_dtype=_compute_dtype(self.precision))
+            o_part.zero_()
+            lse.fill_(float("-inf"))
+        allrec = parallel.gather_packed(record, cache.group)
+        ctx = ops.lse_merge_packed(allrec, dist.get_world_size(cache.group), B, Nq, H, o_dtype=_compute_dtype(self.precision))
         return ctx

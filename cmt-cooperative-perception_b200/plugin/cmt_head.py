@@ -422,14 +422,25 @@ class _CmtHeadBase(nn.Module):
             table[key] = hit
         return hit
 
-    def _rv_pe(self, img_feats, img_metas, mats=None):
-        """cmt_head.py:417-433 -> [B*V,H,W,C] fp32."""
+    def _rv_pe(self, img_feats, img_metas, mats=None, n_bev=0):
+        """cmt_head.py:417-433 -> [B*V,H,W,C] fp32.  Under the KV-token split a rank needs the encodings of its own image
+        tokens only: the MLP (22 GF per frame) then runs on that row range and an RvPosRows is returned."""
         BN, C, H, W = img_feats.shape
         pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
         if mats is None:
             mats = self._matrices(img_metas, img_feats.device)
         dt = _compute_dtype(self.precision)
         coords = ops.ray_pe(mats[1].reshape(-1, 4, 4), H, W, self.depth_num, pad_h, pad_w, self.pc_range, out_dtype=dt)
+        B = len(img_metas)
+        n_img = (BN // B) * H * W
+        lo, hi = self.transformer.kv_token_range(n_bev + n_img)
+        if (lo, hi) != (0, n_bev + n_img):
+            from .cmt_transformer import RvPosRows
+            a, b = max(lo - n_bev, 0), max(hi - n_bev, 0)
+            if b <= a:
+                return RvPosRows(coords.new_zeros((B, 0, self.hidden_dim), dtype=torch.float32), 0, 0)
+            rows = coords.view(B, n_img, -1)[:, a:b].contiguous()
+            return RvPosRows(self._mlp("rv_embedding", rows, tag="rv_pe_mlp"), a, b)
         return self._mlp("rv_embedding", coords, tag="rv_pe_mlp")
 
     def _bev_pos_embed(self, device):
@@ -501,7 +512,8 @@ class _CmtHeadBase(nn.Module):
         query_embeds = self._query_embeds(reference_points, img_metas, mats)
         tr = self.transformer
         bev_pos = self._bev_pos_embed(dev).contiguous() if self._has_bev else None
-        rv_pos = self._rv_pe(x_img, img_metas, mats).contiguous() if self._has_img else None
+        n_bev = x.shape[2] * x.shape[3] if self._has_bev else 0
+        rv_pos = self._rv_pe(x_img, img_metas, mats, n_bev=n_bev).contiguous() if self._has_img else None
         xb = self._apply_shared_conv_to(x).contiguous() if self._has_bev else None
         V = (x_img.shape[0] // B) if self._has_img else 0
         cache, _ = tr.build_kv_cache(xb, x_img.contiguous() if self._has_img else None, bev_pos, rv_pos, B, V)
@@ -516,8 +528,9 @@ class _CmtHeadBase(nn.Module):
         mats = self._matrices(img_metas, dev) if self._has_img else None
         query_embeds = self._query_embeds(reference_points, img_metas, mats)
         if self._has_bev and self._has_img:
+            n_bev = x.shape[2] * x.shape[3]
             x = self._apply_shared_conv_to(x)
-            rv_pos = self._rv_pe(x_img, img_metas, mats)
+            rv_pos = self._rv_pe(x_img, img_metas, mats, n_bev=n_bev)
             outs_dec, _ = self.transformer(x, x_img, query_embeds, self._bev_pos_embed(dev), rv_pos,
                                            attn_masks=attn_mask)
         elif self._has_bev:

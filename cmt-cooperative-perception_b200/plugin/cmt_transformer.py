@@ -22,6 +22,18 @@ def _compute_dtype(precision):
     return torch.float32 if precision == "fp32" else torch.bfloat16
 
 
+class RvPosRows:
+    """Image-token position encodings of a sub-range only: rows [a, b) of every frame's V*h*w image tokens, [B, b-a, C]
+    (a rank of the KV-token split runs the rv-PE MLP on its own tokens).  Stands in for rv_pos_embed."""
+
+    def __init__(self, rows, a, b):
+        self.rows, self.a, self.b = rows, a, b
+
+    def contiguous(self):
+        self.rows = self.rows.contiguous()
+        return self
+
+
 class BevTokenSource:
     """The BEV map BEFORE shared_conv together with the folded conv + BN parameters: handed to the transformer in place
     of the convolved [B,C,H,W] tensor so that the 3x3 convolution runs as a tcgen05 implicit GEMM whose epilogue writes
@@ -111,9 +123,14 @@ class _CmtTransformerBase(nn.Module):
         """gather (K4) + all-layer K / V^T projection (K2).  Returns (KVCache, xv [B,n_tok,C]) where n_tok is
         this rank's share of the token axis (all tokens without the KV-token split)."""
         dt = _compute_dtype(self.precision)
-        n_kv = (x_bev.shape[2] * x_bev.shape[3] if x_bev is not None else 0) + \
-               (V * x_img.shape[2] * x_img.shape[3] if x_img is not None else 0)
+        rv_rows = None
+        n_img_tok = V * x_img.shape[2] * x_img.shape[3] if x_img is not None else 0
+        if isinstance(rv_pos, RvPosRows):
+            rv_pos, rv_rows = rv_pos.rows, (rv_pos.a, rv_pos.b)
+        n_kv = (x_bev.shape[2] * x_bev.shape[3] if x_bev is not None else 0) + n_img_tok
         lo, hi = self.kv_token_range(n_kv)
+        if rv_rows is not None and rv_rows[1] <= rv_rows[0]:
+            x_img, rv_pos, rv_rows, V = None, None, None, 0   # this rank's share holds no image token
         group = self.kv_split_group
         L = len(self.decoder.layers)
         H = self.decoder.layers[0].attentions[-1].num_heads
@@ -136,10 +153,10 @@ class _CmtTransformerBase(nn.Module):
                 ops.shared_conv_tokens(self._xp[1], x_bev.w, x_bev.bias, bev_pos, xk, xv, Hb, Wb, tok_range=(lo, min(hi, n_bev)))
             if x_img is not None and hi > n_bev:
                 ops.gather_tokens(None, x_img, None, rv_pos, B, V, out_dtype=dt, tok_range=(lo, hi), n_bev_reserved=n_bev,
-                                  out=(xk, xv))
+                                  out=(xk, xv), rv_rows=rv_rows)
         else:
             xk, xv = ops.gather_tokens(x_bev, x_img, bev_pos, rv_pos, B, V, out_dtype=dt,
-                                       tok_range=None if group is None else (lo, hi))
+                                       tok_range=None if group is None else (lo, hi), rv_rows=rv_rows)
         wk, bk, wv, bv = self._stacked_kv_weights()
         kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
         k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)

@@ -87,10 +87,13 @@ int cmt_pos2embed(const float* pos, void* out, int N, int pos_stride, int F, int
  * xk = mem + pos, xv = mem, token-major, order BEV tokens then image tokens view-major,
  * N_kv = n_bev + V*n_img.  Only tokens [tok_begin, tok_end) are produced: xk, xv are
  * [B, tok_end - tok_begin, C] (0, N_kv = everything; a sub-range = this rank's share of a KV-token
- * split).  out dtype fp32|bf16. */
+ * split).  rv_rows > 0: rv_pos holds only rows [rv_tok0, rv_tok0 + rv_rows) of every frame's V*n_img image tokens,
+ * [B, rv_rows, C] (the rank computed the rv-PE MLP for its own tokens only); rv_rows = 0: all of them.
+ * out dtype fp32|bf16. */
 int cmt_gather_tokens(const void* x_bev, const void* x_img, const float* bev_pos,
                       const float* rv_pos, void* xk, void* xv, int B, int C, int n_bev, int V,
-                      int n_img, int tok_begin, int tok_end, int feat_dtype, int out_dtype, void* stream);
+                      int n_img, int tok_begin, int tok_end, int rv_tok0, int rv_rows, int feat_dtype, int out_dtype,
+                      void* stream);
 
 /* ---- K2: projection / MLP GEMM ------------------------------------------------------
  * C = act((A * B^T + bias) * alpha); A:[M,K] (lda), B:[N,K] (ldb), both row-major, K contiguous.
@@ -178,9 +181,12 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Log-sum-exp merge of G partial attention results (KV-token split across GPUs or streams):
- * o_parts [G,B,Nq,H*32] fp32, lse_parts [G,B,H,Nq] fp32 (natural log) -> o [B,Nq,H*32], lse. */
+ * part g: o [B,Nq,H*32] fp32 at o_parts + g*o_gstride, lse [B,H,Nq] fp32 (natural log) at lse_parts + g*lse_gstride
+ * (strides in elements; 0 = densely stacked [G,...] arrays) -> o [B,Nq,H*32], lse (nullable).  With
+ * o_gstride = lse_gstride = B*Nq*H*32 + B*H*Nq and lse_parts = o_parts + B*Nq*H*32 the parts are the packed
+ * (O | LSE) records of ONE all-gather per decoder layer. */
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B,
-                  int H, int Nq, int o_dtype, void* stream);
+                  int H, int Nq, int64_t o_gstride, int64_t lse_gstride, int o_dtype, void* stream);
 
 /* ---- decoder small ops: fused residual add + LayerNorm --------------------------------
  * One launch for `query = norm(identity + attn_out)` of mmcv BaseTransformerLayer (post-norm order

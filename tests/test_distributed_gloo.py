@@ -47,6 +47,13 @@ def _worker(rank, world, port, n_kv, q_out):
         o, lse = parallel.merge_partials_reference(o_all, l_all, 8)
         want_o, want_l = _partial_attention(q, k, v, 0, n_kv)
         ok = torch.allclose(o, want_o, atol=1e-5) and torch.allclose(lse, want_l, atol=1e-5)
+        # the packed (O | LSE) record: ONE all-gather per decoder layer carries both (what the GPU path sends)
+        rec = torch.cat([o_p.reshape(-1), l_p.reshape(-1)])
+        allrec = parallel.gather_packed(rec).view(world, -1)
+        n_o = o_p.numel()
+        o2, lse2 = parallel.merge_partials_reference(allrec[:, :n_o].reshape(world, *o_p.shape),
+                                                     allrec[:, n_o:].reshape(world, *l_p.shape), 8)
+        ok = ok and torch.equal(o2, o) and torch.equal(lse2, lse)
         # frame sharding: disjoint contiguous blocks, no collective needed to compute them
         flo, fhi = parallel.shard_frames(13, rank, world)
         mine = torch.zeros(13)
