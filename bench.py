@@ -156,6 +156,7 @@ def cpu_baseline_sample(workload):
     """Bounded CPU sample for the default line: ONE frame of the same workload through the oracle."""
     from oracle import cmt_oracle as O
     from cmtcoop_b200.plugin import build_head
+    prev_threads = torch.get_num_threads()
     torch.set_num_threads(os.cpu_count() or 1)
     kind, cfg, inputs = build_case(workload, 1)
     head = build_head({k: v for k, v in cfg.items() if not k.startswith("_")})
@@ -169,7 +170,9 @@ def cpu_baseline_sample(workload):
         for _ in range(iters):
             O.head_forward(sd, cfg, inputs)
         dt = (time.perf_counter() - t0) / iters
-    return dict(value=1.0 / dt, unit="frames/s", cores=torch.get_num_threads(), kind="port",
+    cores = torch.get_num_threads()
+    torch.set_num_threads(prev_threads)
+    return dict(value=1.0 / dt, unit="frames/s", cores=cores, kind="port",
                 sample=f"1 frame of the same workload per iteration, 1 warm-up + {iters} timed iterations "
                        f"({dt:.2f} s each), fp32, all host threads")
 
@@ -197,10 +200,14 @@ def frame0_inputs(inputs, B, coop, feat_dtype):
 def parity_check(cfg, inputs, B, coop, feat_dtype, head, rets):
     """Frame 0 of the timed workload against the CPU oracle (outside every timed region)."""
     from oracle import cmt_oracle as O
+    prev_threads = torch.get_num_threads()
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
     with torch.no_grad():
         want, _ = O.head_forward(sd, cfg, frame0_inputs(inputs, B, coop, feat_dtype))
+    # back to the launcher's thread count (torchrun: OMP_NUM_THREADS=1): a 24-thread intra-op pool left behind turns
+    # every small host-side tensor op of the serving loop into an oversubscribed OpenMP region (e2e 8.6 -> 42 ms per step)
+    torch.set_num_threads(prev_threads)
     per = {n: O.rel_l2(rets[0][n][:, :1].float().cpu(), want[0][n]) for n in want[0]}
     worst = max(per.values())
     shp = {n: list(want[0][n].shape) for n in ("cls_logits", "center")}
@@ -526,6 +533,12 @@ def main():
         if parity is not None and not parity["ok"]:
             print(f"bench.py: PARITY FAILED: frame 0 rel-L2 {parity['rel_l2']:.3e} > 1e-2", file=sys.stderr, flush=True)
     if world > 1:
+        # graphs that captured NCCL work must be gone before the process group is torn down
+        graphed = graphed2 = runner = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

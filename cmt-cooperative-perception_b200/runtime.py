@@ -127,12 +127,21 @@ class PipelinedRunner:
         if not batches:
             return results
         pending = [None, None]                                      # batch index whose outputs sit in the slot
+        trace = os.environ.get("CMT_RUNNER_TRACE") == "1"           # host-side phase times of every step -> stderr
+        if trace:
+            import sys
+            import time
+            marks = []
         self._enqueue_copy_in(0, batches[0])
         for i, _ in enumerate(batches):
             slot = i & 1
+            if trace:
+                tm = [time.perf_counter()]
             if i + 1 < len(batches):
                 self._enqueue_copy_in(slot ^ 1, batches[i + 1])     # overlaps this step's compute
             cur.wait_event(self.ev_in[slot])
+            if trace:
+                tm.append(time.perf_counter())
             if pending[slot] is not None:
                 # the staging buffers of this slot still hold batch i-2: hand it out before they are overwritten
                 j = pending[slot]
@@ -142,6 +151,8 @@ class PipelinedRunner:
                 if self.keep_results:
                     results[j] = self._collect(slot)
                 pending[slot] = None
+            if trace:
+                tm.append(time.perf_counter())
             if self._primed[slot]:
                 # a graph's static outputs are overwritten by the slot's next replay, and the staging buffers by the
                 # next copy-out: both wait for the copy-out of the slot's previous batch
@@ -149,6 +160,8 @@ class PipelinedRunner:
             rets = self.graphs[slot]() if self.graphs is not None else self._forward(self.dbuf[slot])
             self.ev_free[slot].record(cur)
             self._primed[slot] = True
+            if trace:
+                tm.append(time.perf_counter())
             if self.hout[slot] is None:
                 self.hout[slot] = [{n: torch.empty(t.shape, dtype=t.dtype).pin_memory() for n, t in task.items()}
                                    for task in rets]
@@ -162,6 +175,13 @@ class PipelinedRunner:
                         stage[n].copy_(t, non_blocking=True)
                 self.ev_out[slot].record(self.s_out)
             pending[slot] = i
+            if trace:
+                tm.append(time.perf_counter())
+                marks.append([1e3 * (b - a) for a, b in zip(tm[:-1], tm[1:])])
+        if trace:
+            for i, m in enumerate(marks):
+                print(f"runner step {i}: copy-in enqueue {m[0]:.2f} ms, collect {m[1]:.2f}, forward enqueue {m[2]:.2f}, copy-out enqueue {m[3]:.2f}",
+                      file=sys.stderr, flush=True)
         self.s_out.synchronize()                                    # every device->host copy has landed
         self.s_in.synchronize()
         for slot in (0, 1):

@@ -9,7 +9,7 @@ if [ "$N" = "2" ]; then
 fi
 run() { # name, extra args
   name=$1; shift
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-shared-conv-leg "$@" > gpurun_out/r2_${name}_$N.json 2> gpurun_out/r2_${name}_$N.err
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-shared-conv-leg "$@" > gpurun_out/r2_${name}_$N.json 2> gpurun_out/r2_${name}_$N.err
   echo "$name N=$N exit=$? $(python -c "
 import json,sys
 try:
@@ -19,5 +19,5 @@ except Exception as e: print('ERR',e)
   tail -2 gpurun_out/r2_${name}_$N.err
 }
 run kvsplit --kv-split
-run kvsplit_graph --kv-split --kv-split-graph
+[ "$N" = "2" ] && run kvsplit_graph --kv-split --kv-split-graph
 run shard
