@@ -46,10 +46,11 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of tc_attn_db_kernel per launch from the committed ncu --set full
-# capture (profiles/r1_attn_static_ncu_raw.csv, the static-shift instantiation the bench runs: 1.3950 GB + 0.0118 GB at B=8),
-# per frame.  K+V of one layer are
-# 57.8 MB per frame; the 3 query blocks of a (frame, head) stream them at different times, hence ~3x.
-NCU_DRAM_BYTES_PER_FRAME = {"nusc": (1.394999e9 + 0.011791e9) / 8}
+# capture (profiles/r2_attn_static_ncu_raw.csv, the static-shift instantiation the bench runs: 850.2 MB read + 11.1 MB
+# written at B=8), per frame.  K+V of one layer are 57.8 MB per frame; with the band-aligned partition the first two query
+# blocks of a (frame, head) share one pass over K/V through L2 and the third streams them again: 1.86x the algorithmic
+# bytes (round 1: 3.0x).
+NCU_DRAM_BYTES_PER_FRAME = {"nusc": (850.232832e6 + 11.066368e6) / 8}
 
 
 def build_case(workload, B, seed=0, in_channels=256):

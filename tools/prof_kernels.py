@@ -95,3 +95,13 @@ if which in ("raype", "all"):
     # 64 frames (590 MB of bf16 output: beyond the 126 MB L2, so the time is an HBM write time)
     m64 = torch.eye(4, device=dev).repeat(64 * 6, 1, 1).contiguous()
     timed("raype_b64", lambda: ops.ray_pe(m64, 40, 100, 64, 640.0, 1600.0, [-54, -54, -5, 54, 54, 3]))
+if which == "conv":   # shared_conv implicit GEMM at the config-3 shape (8 frames, 512 -> 256 channels, 180 x 180)
+    x = torch.randn(B, 512, 180, 180, device=dev).bfloat16()
+    w = (torch.randn(256, 9 * 512, device=dev) / 68).bfloat16()
+    bias = torch.randn(256, device=dev)
+    pos = torch.randn(180 * 180, 256, device=dev)
+    xk = torch.empty((B, N_kv, 256), dtype=torch.bfloat16, device=dev)
+    xv = torch.empty_like(xk)
+    xp = ops.nchw_to_padded_nhwc(x)
+    timed("nchw_to_padded_nhwc", lambda: ops.nchw_to_padded_nhwc(x, xp))
+    timed("shared_conv", lambda: ops.shared_conv_tokens(xp, w, bias, pos, xk, xv, 180, 180))
