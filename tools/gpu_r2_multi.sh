@@ -21,3 +21,6 @@ except Exception as e: print('ERR',e)
 run kvsplit --kv-split
 [ "$N" = "2" ] && run kvsplit_graph --kv-split --kv-split-graph
 run shard
+# host->device ceiling of this box: every rank copies 133 MB of pinned memory at the same time (no compute)
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tools/e2e_probe2.py 2>&1 | grep "rank" | sort > gpurun_out/r2_h2d_probe_$N.txt
+echo "h2d probe N=$N: $(grep -c 'H2D 133MB' gpurun_out/r2_h2d_probe_$N.txt) lines; $(grep 'H2D 133MB' gpurun_out/r2_h2d_probe_$N.txt | tail -1)"
