@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cmtcoop_b200.h")
 
 CMT_F32, CMT_BF16, CMT_F16, CMT_BF16_SIMT = 0, 1, 2, 3
 GEMM_RELU, GEMM_BIAS_PER_ROW, GEMM_FORCE_SIMT, GEMM_TRANSPOSE_OUT = 1, 2, 4, 8
+LN_X_ROW_BROADCAST = 1
 
 _c = ctypes
 _vp, _i, _i64, _f, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -40,7 +41,7 @@ SIGNATURES = {
                                 _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
     "cmt_lse_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i, _vp]),
     "cmt_coop_max": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "cmt_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cmt_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cmt_task_head_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cmt_split3_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i64, _vp]),
     "cmt_debug_attn_timing": (_i, [_vp]),

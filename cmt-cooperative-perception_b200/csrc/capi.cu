@@ -400,9 +400,9 @@ int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* 
 
 int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                       float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
-                      void* yadd, int lp_dtype, void* stream) {
+                      void* yadd, int lp_dtype, int flags, void* stream) {
     CMT_REQUIRE_DEVICE();
-    return launch_add_layernorm(x, r, gamma, beta, eps, M, C, y, gamma2, beta2, y2, add, ylp, yadd, lp_dtype,
+    return launch_add_layernorm(x, r, gamma, beta, eps, M, C, y, gamma2, beta2, y2, add, ylp, yadd, lp_dtype, flags,
                                 static_cast<cudaStream_t>(stream));
 }
 

@@ -70,7 +70,7 @@ int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, floa
 // norm_kernels.cu
 int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
-                         void* yadd, int lp_dtype, cudaStream_t stream);
+                         void* yadd, int lp_dtype, int flags, cudaStream_t stream);
 int launch_task_head_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* out,
                           int L, int M, int NH, int HC, int CMAX, float eps, int ksize, int Nq, const float* ref_logit,
                           const int* dec_comp, const float* dec_scale, const float* dec_offset, const long long* head_off_host,

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             float* __restrict__ y, const float* __restrict__ gamma2,
                                                             const float* __restrict__ beta2, float* __restrict__ y2,
                                                             const float* __restrict__ add, void* __restrict__ ylp,
-                                                            void* __restrict__ yadd) {
+                                                            void* __restrict__ yadd, int x_row_broadcast) {
     constexpr int C = kPerLane * 32;
     pdl_trigger();
     pdl_wait();
@@ -25,13 +25,14 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     const int warps_per_block = blockDim.x >> 5;
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
         const long long base = static_cast<long long>(row) * C;
+        const long long xbase = x_row_broadcast ? 0 : base;   // x is ONE row shared by every output row
         float v[kPerLane];
         float s = 0.f;
         // lane owns 4-element groups: element index = (g * 32 + lane) * 4 + e  (coalesced 16 B accesses)
 #pragma unroll
         for (int g = 0; g < kPerLane / 4; ++g) {
             const int idx = (g * 32 + lane) * 4;
-            float4 a = *reinterpret_cast<const float4*>(x + base + idx);
+            float4 a = *reinterpret_cast<const float4*>(x + xbase + idx);
             if (r != nullptr) {
                 const float4 b = *reinterpret_cast<const float4*>(r + base + idx);
                 a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
 
 int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
-                         void* yadd, int lp_dtype, cudaStream_t stream) {
+                         void* yadd, int lp_dtype, int flags, cudaStream_t stream) {
     CMT_CHECK_ARG(x && gamma && beta && y && M > 0, "cmt_add_layernorm: bad arguments");
+    const int x_row_broadcast = (flags & CMT_LN_X_ROW_BROADCAST) ? 1 : 0;
     CMT_CHECK_ARG(C == 256, "cmt_add_layernorm: embed dim 256 only (got %d)", C);
     CMT_CHECK_ARG(y2 == nullptr || (gamma2 && beta2), "cmt_add_layernorm: second norm needs gamma2/beta2");
     CMT_CHECK_ARG(yadd == nullptr || add != nullptr, "cmt_add_layernorm: yadd needs add");
@@ -122,10 +124,10 @@ int launch_add_layernorm(const float* x, const float* r, const float* gamma, con
     if (blocks > cap) blocks = cap;
     if (lp_dtype == CMT_BF16)
         launch_pdl(add_layernorm_kernel<8, true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, x, r, gamma, beta, eps, M, y, gamma2,
-                                                                                   beta2, y2, add, ylp, yadd);
+                                                                                   beta2, y2, add, ylp, yadd, x_row_broadcast);
     else
         launch_pdl(add_layernorm_kernel<8, false>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, x, r, gamma, beta, eps, M, y, gamma2,
-                                                                                    beta2, y2, add, ylp, yadd);
+                                                                                    beta2, y2, add, ylp, yadd, x_row_broadcast);
     CMT_LAUNCH_CHECK("cmt_add_layernorm");
     return CMT_OK;
 }

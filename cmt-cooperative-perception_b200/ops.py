@@ -514,22 +514,28 @@ def coop_max(a, b):
 
 
 def add_layernorm(x, r, gamma, beta, eps=1e-5, *, gamma2=None, beta2=None, y2=None, add=None, lp_dtype=None,
-                  want_ylp=False, want_yadd=False):
+                  want_ylp=False, want_yadd=False, rows=None):
     """Fused residual add + LayerNorm (+ optional second LayerNorm, + low-precision copies of y and y+add).
     x, r, add: [..., 256] fp32.  Returns (y, y2, ylp, yadd) with None for outputs not requested."""
     x = _cuda(x, "x", torch.float32)
     C = x.shape[-1]
-    M = x.numel() // C
-    y = torch.empty_like(x)
+    flags = 0
+    shape = x.shape
+    if rows is not None:   # x is ONE row [C] shared by every row of the [*rows, C] output
+        assert x.numel() == C and r is None
+        flags = _lib.LN_X_ROW_BROADCAST
+        shape = (*rows, C)
+    M = int(math.prod(shape[:-1]))
+    y = torch.empty(shape, dtype=torch.float32, device=x.device)
     if y2 is None and gamma2 is not None:
-        y2 = torch.empty_like(x)
+        y2 = torch.empty_like(y)
     lp_dtype = lp_dtype or torch.float32
-    ylp = torch.empty(x.shape, dtype=lp_dtype, device=x.device) if want_ylp else None
-    yadd = torch.empty(x.shape, dtype=lp_dtype, device=x.device) if want_yadd else None
+    ylp = torch.empty(shape, dtype=lp_dtype, device=x.device) if want_ylp else None
+    yadd = torch.empty(shape, dtype=lp_dtype, device=x.device) if want_yadd else None
     lib = _lib.load()
     with torch.cuda.device(x.device):
         rc = lib.cmt_add_layernorm(_ptr(x), _ptr(r), _ptr(gamma), _ptr(beta), float(eps), M, C, _ptr(y), _ptr(gamma2),
-                                   _ptr(beta2), _ptr(y2), _ptr(add), _ptr(ylp), _ptr(yadd), _dt(lp_dtype), _stream(x))
+                                   _ptr(beta2), _ptr(y2), _ptr(add), _ptr(ylp), _ptr(yadd), _dt(lp_dtype), flags, _stream(x))
     _lib.check(rc, "cmt_add_layernorm")
     _count()
     return y, y2, ylp, yadd

@@ -25,6 +25,10 @@ from .attention import KVCache, _Q_SCALE, _compute_dtype
 
 _STD_ORDER = ("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")
 
+# Decoder layer 0 attends over an all-zero target: its self-attention is the constant row out_proj(b_v) (see _run).  False
+# runs the five launches anyway (tests compare the two).
+SKIP_ZERO_TARGET_SELF_ATTENTION = True
+
 # diagnostics for bench.py: the operand-norm maxima of the last forward, (q_norm2 [L,B,H], [k_norm2 [B_i,L,H] per cache]) or None.
 # An attention item (layer, frame, head) takes the static-shift kernel iff sqrt(qn * kn) * 1.0079 + 1e-3 <= 60.
 last_norms = None
@@ -117,9 +121,11 @@ def _run(decoder, query_pos, caches, precision):
     out = torch.empty((L, B, Nq, C), dtype=torch.float32, device=dev)
     pw, pb, peps = _ln(decoder.post_norm)
 
-    x = torch.zeros((B, Nq, C), dtype=torch.float32, device=dev)   # target = zeros (cmt_transformer.py:114)
-    x_lp = torch.zeros((B, Nq, C), dtype=dt, device=dev)           # cast(x)
-    xq_lp = query_pos.to(dt)                                       # cast(x + query_pos)
+    x = x_lp = xq_lp = None
+    if not SKIP_ZERO_TARGET_SELF_ATTENTION:
+        x = torch.zeros((B, Nq, C), dtype=torch.float32, device=dev)   # target = zeros (cmt_transformer.py:114)
+        x_lp = torch.zeros((B, Nq, C), dtype=dt, device=dev)           # cast(x)
+        xq_lp = query_pos.to(dt)                                       # cast(x + query_pos)
 
     # max |q|^2 per (layer, frame, head) of the cross-attention queries: with cache.k_norm2 the attention kernel gets a
     # bound on every score and drops the running row maximum (ops.cross_attn)
@@ -131,13 +137,22 @@ def _run(decoder, query_pos, caches, precision):
     for li, layer in enumerate(decoder.layers):
         # ---- self-attention over the queries: q = k = x + query_pos, v = x (key_pos = query_pos) ----
         sw = _mha_weights(layer.attentions[0].attn, dt)
-        q = ops.linear(xq_lp, sw["wq"], sw["bq"], alpha=_Q_SCALE, out_dtype=dt)
-        k = ops.project_keys(xq_lp, sw["wk"], sw["bk"], 1, H)
-        vt = ops.project_values_t(x_lp, sw["wv"], sw["bv"], 1, H)
-        ctx = ops.cross_attn(q, k, vt, 0, tag="self_attn")
-        sa = ops.linear(ctx, sw["wo"], sw["bo"], out_dtype=torch.float32)
         g, b, eps = _ln(layer.norms[0])
-        x1, _, _, x1q_lp = ops.add_layernorm(x, sa, g, b, eps, add=query_pos, lp_dtype=dt, want_yadd=True)
+        if li == 0 and SKIP_ZERO_TARGET_SELF_ATTENTION:
+            # The first layer's target is zero (cmt_transformer.py:114): every value row is the value bias b_v, so the
+            # softmax-weighted mean is b_v for every query whatever the attention weights, and the block's output is the
+            # single row out_proj(b_v) (operands rounded like the kernels round them).  x + attn_out is that row.
+            sa_row = _cached(layer.attentions[0].attn, "zero_target_row", (dt,) + _pkey(*layer.attentions[0].attn.parameters()),
+                             lambda: (sw["bv"].to(dt).float() @ sw["wo"].float().t() + sw["bo"]).contiguous())
+            x1, _, _, x1q_lp = ops.add_layernorm(sa_row, None, g, b, eps, add=query_pos, lp_dtype=dt, want_yadd=True,
+                                                 rows=(B, Nq))
+        else:
+            q = ops.linear(xq_lp, sw["wq"], sw["bq"], alpha=_Q_SCALE, out_dtype=dt)
+            k = ops.project_keys(xq_lp, sw["wk"], sw["bk"], 1, H)
+            vt = ops.project_values_t(x_lp, sw["wv"], sw["bv"], 1, H)
+            ctx = ops.cross_attn(q, k, vt, 0, tag="self_attn")
+            sa = ops.linear(ctx, sw["wo"], sw["bo"], out_dtype=torch.float32)
+            x1, _, _, x1q_lp = ops.add_layernorm(x, sa, g, b, eps, add=query_pos, lp_dtype=dt, want_yadd=True)
         # ---- cross-attention over the hoisted K/V cache ----
         mha = layer.attentions[1].attn
         cw = mha.compute_weights()

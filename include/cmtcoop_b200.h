@@ -39,6 +39,9 @@ extern "C" {
 #define CMT_GEMM_FORCE_SIMT 4    /* fp32 CUDA-core kernel even for bf16 operands       */
 #define CMT_GEMM_TRANSPOSE_OUT 8 /* store C^T inside each column block (bf16 tensor-core path only) */
 
+/* flags of cmt_add_layernorm */
+#define CMT_LN_X_ROW_BROADCAST 1 /* x is ONE row [C] shared by all M rows (decoder layer 0: see cmt_add_layernorm) */
+
 int cmt_version(void);
 const char* cmt_last_error_string(void);
 /* 0 when device `dev` is sm_100 (B200), CMT_ERR_ARCH otherwise. */
@@ -195,10 +198,13 @@ int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* 
  * next projection needs.  x, r (nullable), add (nullable): [M,C] fp32; C must be 256.
  *   y    = LN(x + r; gamma, beta, eps)            fp32, required
  *   y2   = LN(y; gamma2, beta2, eps)              fp32, optional (NULL)
- *   ylp  = cast(y), yadd = cast(y + add)          lp_dtype (fp32|bf16), each optional (NULL) */
+ *   ylp  = cast(y), yadd = cast(y + add)          lp_dtype (fp32|bf16), each optional (NULL)
+ * flags & CMT_LN_X_ROW_BROADCAST: x is a single row [C] used for every output row.  Decoder layer 0 runs on the zero
+ * target (cmt_transformer.py:114), so its self-attention attends over values that are all equal to the value bias and
+ * returns out_proj(b_v) for every query whatever the weights of the softmax: that one row is the whole `x + attn_out`. */
 int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps,
                       int M, int C, float* y, const float* gamma2, const float* beta2, float* y2,
-                      const float* add, void* ylp, void* yadd, int lp_dtype, void* stream);
+                      const float* add, void* ylp, void* yadd, int lp_dtype, int flags, void* stream);
 
 /* ---- task heads -------------------------------------------------------------------------
  * SeparateTaskHead (models/dense_heads/cmt_head.py:97-203 with GroupLayerNorm1d :53-94) for all output heads at once,

@@ -83,3 +83,27 @@ def test_flash_mha_key_padding_mask(precision, tol):
         out, _ = mha(q.to(DEV), k.to(DEV), v.to(DEV), key_padding_mask=keep.to(DEV))
     want = O.mha(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), sd, "a", num_heads=H, key_keep=keep).transpose(0, 1)
     assert O.rel_l2(out.cpu(), want) < tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-3)])
+def test_zero_target_self_attention_shortcut(precision, tol):
+    """Decoder layer 0 attends over the all-zero target (cmt_transformer.py:114): its self-attention block returns
+    out_proj(b_v) for every query.  The one-row shortcut equals running the five launches."""
+    from cmtcoop_b200.plugin import fused_decoder
+    kind = "CmtHead"
+    cfg, inputs = synth.mini_case(kind)
+    head = build_head(cfg)
+    synth.load_synth_weights(head, 0)
+    head = head.to(DEV).eval().set_precision(precision)
+    d = {k: (torch.from_numpy(v).to(DEV) if isinstance(v, np.ndarray) else v) for k, v in inputs.items()}
+    outs = {}
+    for skip in (True, False):
+        fused_decoder.SKIP_ZERO_TARGET_SELF_ATTENTION = skip
+        n0 = ops.launch_count()
+        with torch.no_grad():
+            outs[skip] = head.forward_single(d["pts_feats"], d["img_feats"], d["img_metas"])
+        outs[skip] = (outs[skip], ops.launch_count() - n0)
+    fused_decoder.SKIP_ZERO_TARGET_SELF_ATTENTION = True
+    assert outs[True][1] < outs[False][1]
+    for name in outs[True][0][0]:
+        assert O.rel_l2(outs[True][0][0][name].float().cpu(), outs[False][0][0][name].float().cpu()) < tol, name
