@@ -200,10 +200,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef CMT_SPIN_LIMIT
 #define CMT_SPIN_LIMIT (1u << 24)
 #endif
+#ifdef CMT_TRAP_REPORT
+// debug builds: before trapping, record which barrier timed out into a HOST-mapped buffer (it survives the dead context):
+// cmt_dbg_host[0] = record count, then 4 words per record: blockIdx | warp << 16, barrier smem offset, parity, line
+static __device__ unsigned long long* cmt_dbg_host = nullptr;
+#define CMT_WAIT_TIMEOUT(bar, parity)                                                                              \
+    do {                                                                                                           \
+        if ((threadIdx.x & 31) == 0 && cmt_dbg_host != nullptr) {                                                  \
+            const unsigned long long k = atomicAdd(cmt_dbg_host, 1ull);                                            \
+            if (k < 500) {                                                                                         \
+                cmt_dbg_host[1 + 4 * k] = blockIdx.x | (static_cast<unsigned long long>(threadIdx.x >> 5) << 16);  \
+                cmt_dbg_host[2 + 4 * k] = smem_u32(bar) & 0xffff;                                                  \
+                cmt_dbg_host[3 + 4 * k] = parity;                                                                  \
+                cmt_dbg_host[4 + 4 * k] = __LINE__;                                                                \
+            }                                                                                                      \
+            __threadfence_system();                                                                                \
+        }                                                                                                          \
+        __trap();                                                                                                  \
+    } while (0)
+#else
+#define CMT_WAIT_TIMEOUT(bar, parity) __trap()   // surfaces as cudaErrorLaunchFailure
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > CMT_SPIN_LIMIT) __trap();  // surfaces as cudaErrorLaunchFailure
+        if (++spins > CMT_SPIN_LIMIT) CMT_WAIT_TIMEOUT(bar, parity);
     }
 }
 // Latency-tolerant waiters (producers, issuers that run a buffer ahead): let the hardware suspend the warp
@@ -220,7 +241,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
             : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
         if (ok) break;
-        if (++spins > CMT_SPIN_LIMIT) __trap();
+        if (++spins > CMT_SPIN_LIMIT) CMT_WAIT_TIMEOUT(bar, parity);
     }
 }
 
