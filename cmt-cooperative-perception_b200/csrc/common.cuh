@@ -202,22 +202,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
 #ifdef CMT_TRAP_REPORT
 // debug builds: before trapping, record which barrier timed out into a HOST-mapped buffer (it survives the dead context):
-// cmt_dbg_host[0] = record count, then 4 words per record: blockIdx | warp << 16, barrier smem offset, parity, line
+// cmt_dbg_host[0] = record count, then 4 words per record: blockIdx | warp << 16, barrier smem offset, parity, line.
+// Out of line, so that the wait loops compile as they do with the plain trap.
 static __device__ unsigned long long* cmt_dbg_host = nullptr;
-#define CMT_WAIT_TIMEOUT(bar, parity)                                                                              \
-    do {                                                                                                           \
-        if ((threadIdx.x & 31) == 0 && cmt_dbg_host != nullptr) {                                                  \
-            const unsigned long long k = atomicAdd(cmt_dbg_host, 1ull);                                            \
-            if (k < 500) {                                                                                         \
-                cmt_dbg_host[1 + 4 * k] = blockIdx.x | (static_cast<unsigned long long>(threadIdx.x >> 5) << 16);  \
-                cmt_dbg_host[2 + 4 * k] = smem_u32(bar) & 0xffff;                                                  \
-                cmt_dbg_host[3 + 4 * k] = parity;                                                                  \
-                cmt_dbg_host[4 + 4 * k] = __LINE__;                                                                \
-            }                                                                                                      \
-            __threadfence_system();                                                                                \
-        }                                                                                                          \
-        __trap();                                                                                                  \
-    } while (0)
+static __device__ __noinline__ void cmt_wait_timeout(uint32_t bar_off, uint32_t parity, int line) {
+    if ((threadIdx.x & 31) == 0 && cmt_dbg_host != nullptr) {
+        const unsigned long long k = atomicAdd(cmt_dbg_host, 1ull);
+        if (k < 500) {
+            cmt_dbg_host[1 + 4 * k] = blockIdx.x | (static_cast<unsigned long long>(threadIdx.x >> 5) << 16);
+            cmt_dbg_host[2 + 4 * k] = bar_off;
+            cmt_dbg_host[3 + 4 * k] = parity;
+            cmt_dbg_host[4 + 4 * k] = line;
+        }
+        __threadfence_system();
+    }
+    __trap();
+}
+#define CMT_WAIT_TIMEOUT(bar, parity) cmt_wait_timeout(smem_u32(bar) & 0xffff, parity, __LINE__)
 #else
 #define CMT_WAIT_TIMEOUT(bar, parity) __trap()   // surfaces as cudaErrorLaunchFailure
 #endif
