@@ -235,6 +235,9 @@ def main():
     ap.add_argument("--kv-split-graph", action="store_true",
                     help="with --kv-split: capture the forward INCLUDING the per-layer NCCL all-gathers in a CUDA graph")
     ap.add_argument("--no-shared-conv-leg", action="store_true", help="skip the second scope (step including shared_conv)")
+    ap.add_argument("--kv-split-peer", action="store_true",
+                    help="with --kv-split: per-layer exchange + merge as ONE kernel over peer memory (NVLink loads) instead of "
+                         "NCCL all-gather + merge")
     ap.add_argument("--kv-split", action="store_true",
                     help="BASELINE configs[4] variant: every rank sees the SAME frames and attends 1/N of the K/V tokens; "
                          "one NCCL all-gather of (O, LSE) per decoder layer + log-sum-exp merge (strong scaling)")
@@ -265,15 +268,16 @@ def main():
     B = args.batch
     fdt = FEAT_DTYPES[args.feat_dtype]
     kv_split = args.kv_split and world > 1
-    if kv_split and not args.kv_split_graph:
-        args.no_cuda_graph = True   # default: the per-layer NCCL all-gather stays outside graph capture
+    if kv_split and not (args.kv_split_graph or args.kv_split_peer):
+        args.no_cuda_graph = True   # default: the per-layer NCCL all-gather stays outside graph capture (the peer-memory
+                                    # exchange is an ordinary kernel and replays from the graph like the rest)
     kind, cfg, inputs = build_case(args.workload, B, seed=0 if kv_split else rank)
     head = build_head({k: v for k, v in cfg.items() if not k.startswith("_")})
     synth.load_synth_weights(head, 0)
     head = head.to(dev).eval().set_precision("bf16")
     head.apply_shared_conv = False
     if kv_split:
-        head.transformer.enable_kv_split()
+        head.transformer.enable_kv_split(peer_memory=args.kv_split_peer)
     coop = kind.endswith("Coop")
     feat_keys = [k for k, v in inputs.items() if isinstance(v, np.ndarray)]
     with numa_local_to_gpu(local_rank) as numa:
@@ -368,6 +372,7 @@ def main():
         parity = None
         if rank == 0 and not args.no_parity:
             parity = parity_check(cfg, inputs, B, coop, fdt, head, rets)
+        barrier()   # rank 0 spent seconds in the CPU oracle: nobody starts a forward whose exchange it would keep waiting
 
         # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of every task-head tensor ----
         # public serving API: cmtcoop_b200.runtime.PipelinedRunner double-buffers the H2D of step i+1 and
@@ -498,14 +503,21 @@ def main():
 
         n_nodes = len(nodes)
         hb, tp = pk["hbm_gbs"], pk["bf16_tflops_sustained"]
-        kline("ray_pe", "ray_pe_kernel (K1)", "hbm", B * N_img * 192 * 2.0, hb,
+        # under the KV-token split every token-shaped kernel works on the rank's rows only
+        n_bev_tok = N_kv - N_img
+        img_rank = float(N_img)
+        bev_rank = float(n_bev_tok)
+        if kv_split:
+            img_rank = float(max(0, hi - max(lo, int(n_bev_tok))))
+            bev_rank = float(max(0, min(hi, int(n_bev_tok)) - lo))
+        kline("ray_pe", "ray_pe_kernel (K1)", "hbm", B * img_rank * 192 * 2.0, hb,
               note="at 8 frames the 74 MB output is L2-resident and the launch is ~20 us; profiles/ holds the 64-frame run")
         kline("gather_tokens", "gather_tokens_kernel (K4)", "hbm",
-              B * N_kv * 256 * fsz + B * N_img * 256 * 4 + (N_kv - N_img) * 256 * 4 + 2 * B * N_kv_rank * 256 * 2, hb)
+              B * N_kv_rank * 256 * fsz + B * img_rank * 256 * 4 + bev_rank * 256 * 4 + 2 * B * N_kv_rank * 256 * 2, hb)
         kline("k_proj", "tc_gemm_kernel K projection, all layers", "tensor", 2.0 * B * N_kv_rank * 256 * 1536, tp)
         kline("v_proj", "tc_gemm_kernel V^T projection, all layers", "tensor", 2.0 * B * N_kv_rank * 256 * 1536, tp)
-        kline("rv_pe_mlp.0", "tc_gemm_kernel rv-PE MLP layer 1", "tensor", 2.0 * B * N_img * 192 * 1024, tp)
-        kline("rv_pe_mlp.2", "tc_gemm_kernel rv-PE MLP layer 2", "tensor", 2.0 * B * N_img * 1024 * 256, tp)
+        kline("rv_pe_mlp.0", "tc_gemm_kernel rv-PE MLP layer 1", "tensor", 2.0 * B * img_rank * 192 * 1024, tp)
+        kline("rv_pe_mlp.2", "tc_gemm_kernel rv-PE MLP layer 2", "tensor", 2.0 * B * img_rank * 1024 * 256, tp)
         del n_nodes
 
     if rank == 0:
@@ -518,8 +530,11 @@ def main():
                     dtype="bf16", data="synthetic",
                     config=dict(workload=WORKLOADS[args.workload][3], frames_per_gpu=B,
                                 global_batch=B if kv_split else B * world,
-                                parallelism=(f"K/V tokens split x{world}: queries replicated, one NCCL all-gather of "
-                                             "(O, LSE) per decoder layer + LSE merge" if kv_split else
+                                parallelism=((f"K/V tokens split x{world}: queries replicated, (O, LSE) records exchanged and "
+                                              "merged per decoder layer by one kernel over peer memory (NVLink loads, no NCCL "
+                                              "call on the data path)" if args.kv_split_peer else
+                                              f"K/V tokens split x{world}: queries replicated, one NCCL all-gather of "
+                                              "(O, LSE) per decoder layer + LSE merge") if kv_split else
                                              f"frame sharding x{world}, no data-path collective"),
                                 feature_dtype=args.feat_dtype,
                                 l2="inputs (%.0f MB per step) exceed the 126 MB L2" % (h2d / 1e6),

@@ -398,6 +398,12 @@ int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* 
                             static_cast<cudaStream_t>(stream));
 }
 
+int cmt_lse_merge_peer(const void* const* records, void* const* ctx, void* const* arrive, void* state, int rank, int G,
+                       int B, int H, int Nq, int o_dtype, int scatter, void* stream) {
+    CMT_REQUIRE_DEVICE();
+    return launch_lse_merge_peer(records, ctx, arrive, state, rank, G, B, H, Nq, o_dtype, scatter, static_cast<cudaStream_t>(stream));
+}
+
 int cmt_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                       float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,
                       void* yadd, int lp_dtype, int flags, void* stream) {

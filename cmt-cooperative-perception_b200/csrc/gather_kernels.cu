@@ -347,4 +347,202 @@ int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, floa
     return CMT_OK;
 }
 
+// ---------------------------------------------------------------------------
+// KV-token split: exchange + merge + redistribution in ONE kernel over peer memory (NVLink / NVSwitch loads and stores,
+// no NCCL call on the path).  Every rank keeps its packed (O | LSE) record of the layer, and a context buffer, in memory
+// mapped into all ranks of the group (torch symmetric memory on the host side).  The kernel is a reduce-scatter and an
+// all-gather folded around the merge:
+//   1. announce "my record of exchange `seq` is complete" to every rank: fence.sys + one 32-bit store per peer into
+//      that peer's arrival counters (the record was written by the preceding kernels of this stream),
+//   2. wait until every rank has announced `seq` (acquire loads of the rank's OWN counters: local memory, no NVLink polling),
+//   3. merge 1/G of the rows: the thread reads the G records' values for its 4 elements -- G - 1 of them through NVLink --
+//      and stores the merged result into EVERY rank's context buffer (G - 1 remote stores of 8 or 16 bytes, coalesced),
+//   4. the last block to finish announces "my rows are in your context buffer" to every rank, waits for the same from all
+//      of them and publishes the exchange number; when the kernel ends the local context buffer is complete.
+// Per rank and exchange NVLink carries (G-1)/G of a record in and (G-1)/G of a context out (7.6 MB + 3.7 MB at the bench
+// shape whatever G is), where an all-gather of records delivers (G-1) records (53 MB at G = 8).
+// `seq` lives in device memory (state[0]; state[1] counts finished blocks), so the kernel replays unchanged from a CUDA
+// graph.  Reuse: a rank announces exchange e + 1 only after its kernel of exchange e has completed, hence (a) a record
+// slot may be rewritten as soon as its owner has passed the NEXT exchange -- consecutive exchanges must use different
+// record slots, which the host guarantees (one slot per decoder layer, at least two) -- and (b) peers write exchange
+// e + 1's context only after the local consumer of context e (earlier in this stream than kernel e + 1) has finished.
+constexpr int MAX_PEERS = 8;
+struct PeerMergeParams {
+    const float* rec[MAX_PEERS];        // rank g's record of this exchange (peer-mapped)
+    void* ctx[MAX_PEERS];               // rank g's context buffer of this exchange (peer-mapped)
+    unsigned int* arrive[MAX_PEERS];    // rank g's counters (peer-mapped): [0..7] record announced by rank r, [8..15] context rows written by rank r
+    unsigned int* state;                // local {seq, done_blocks}
+    long long lse_off;                  // element offset of the LSE block inside a record
+    long long t_begin, t_end;           // this rank's share of the B*Nq*H*8 four-element groups
+    int rank, G, B, H, Nq;
+};
+
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys_f(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// all ranks' counters `which` (0: records, 8: context rows) must reach seq; called by threads < G; ~30 s, then trap
+// (a rank that never arrives must not hang the box)
+__device__ __forceinline__ void peer_wait(const unsigned int* flag, unsigned int seq) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - seq) >= 0) break;
+        __nanosleep(100);
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 30000000000ull) __trap();
+        }
+    }
+}
+
+// kScatter = false (small groups): every rank merges ALL rows from the G records (G - 1 records over NVLink) into its own
+// context buffer; steps 3b / 4 disappear and the exchange costs one handshake instead of two.
+template <bool kBf16, bool kScatter>
+__global__ void __launch_bounds__(256) lse_merge_peer_kernel(const PeerMergeParams p) {
+    __shared__ unsigned int seq_s;
+    __shared__ int last_s;
+    if (threadIdx.x == 0) {
+        unsigned int seq;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seq) : "l"(p.state) : "memory");
+        seq_s = seq + 1;
+    }
+    __syncthreads();
+    const unsigned int seq = seq_s;
+    if (blockIdx.x == 0 && threadIdx.x < p.G) {
+        __threadfence_system();   // the record (written by earlier kernels of this stream) before the announcement
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.arrive[threadIdx.x] + p.rank), "r"(seq) : "memory");
+    }
+    if (threadIdx.x < p.G) peer_wait(p.arrive[p.rank] + threadIdx.x, seq);
+    __syncthreads();
+    for (long long t = p.t_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < p.t_end;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int h = static_cast<int>((t >> 3) % p.H);
+        const int n = static_cast<int>(((t >> 3) / p.H) % p.Nq);
+        const int b = static_cast<int>((t >> 3) / (static_cast<long long>(p.H) * p.Nq));
+        const long long li = p.lse_off + (static_cast<long long>(b) * p.H + h) * p.Nq + n;
+        float l[MAX_PEERS];
+        float4 x[MAX_PEERS];
+        // all loads first: G independent round trips in flight per thread
+#pragma unroll
+        for (int g = 0; g < MAX_PEERS; ++g) {
+            if (g < p.G) {
+                l[g] = ld_sys_f(p.rec[g] + li);
+                x[g] = ld_sys_f4(p.rec[g] + 4 * t);
+            }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < MAX_PEERS; ++g)
+            if (g < p.G) mx = fmaxf(mx, l[g]);
+        float den = 0.0f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < MAX_PEERS; ++g) {
+            if (g < p.G) {
+                const float w = (l[g] == -INFINITY) ? 0.0f : __expf(l[g] - mx);
+                den += w;
+                acc.x = fmaf(w, x[g].x, acc.x);
+                acc.y = fmaf(w, x[g].y, acc.y);
+                acc.z = fmaf(w, x[g].z, acc.z);
+                acc.w = fmaf(w, x[g].w, acc.w);
+            }
+        }
+        const float inv = den > 0.0f ? 1.0f / den : 0.0f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        if (kBf16) {
+            uint2 w;
+            w.x = pack_bf16x2(acc.x, acc.y);
+            w.y = pack_bf16x2(acc.z, acc.w);
+            if (!kScatter) {
+                reinterpret_cast<uint2*>(p.ctx[0])[t] = w;
+            } else {
+#pragma unroll
+                for (int g = 0; g < MAX_PEERS; ++g)
+                    if (g < p.G) reinterpret_cast<uint2*>(p.ctx[g])[t] = w;
+            }
+        } else {
+            if (!kScatter) {
+                reinterpret_cast<float4*>(p.ctx[0])[t] = acc;
+            } else {
+#pragma unroll
+                for (int g = 0; g < MAX_PEERS; ++g)
+                    if (g < p.G) reinterpret_cast<float4*>(p.ctx[g])[t] = acc;
+            }
+        }
+    }
+    // the last block to finish tells every rank that this rank's rows have landed, waits for the same from everybody,
+    // and publishes the exchange number for the next launch
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = atomicAdd(p.state + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last_s) return;
+    if (kScatter && threadIdx.x < p.G) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.arrive[threadIdx.x] + 8 + p.rank), "r"(seq) : "memory");
+        peer_wait(p.arrive[p.rank] + 8 + threadIdx.x, seq);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.state[1] = 0;
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.state), "r"(seq) : "memory");
+    }
+}
+
+int launch_lse_merge_peer(const void* const* records, void* const* ctx, void* const* arrive, void* state, int rank, int G,
+                          int B, int H, int Nq, int o_dtype, int scatter, cudaStream_t stream) {
+    CMT_CHECK_ARG(records && ctx && arrive && state, "cmt_lse_merge_peer: null pointer");
+    CMT_CHECK_ARG(G > 0 && G <= MAX_PEERS && rank >= 0 && rank < G, "cmt_lse_merge_peer: 1 <= G <= 8, 0 <= rank < G");
+    CMT_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "cmt_lse_merge_peer: bad shape");
+    CMT_CHECK_ARG(o_dtype == CMT_BF16 || o_dtype == CMT_F32, "cmt_lse_merge_peer: bad dtype");
+    PeerMergeParams p{};
+    for (int g = 0; g < G; ++g) {
+        CMT_CHECK_ARG(records[g] && arrive[g] && ctx[g] && (reinterpret_cast<uintptr_t>(records[g]) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(ctx[g]) & 15) == 0,
+                      "cmt_lse_merge_peer: records / contexts must be non-null and 16-byte aligned");
+        p.rec[g] = static_cast<const float*>(records[g]);
+        p.ctx[g] = ctx[g];
+        p.arrive[g] = static_cast<unsigned int*>(arrive[g]);
+    }
+    p.state = static_cast<unsigned int*>(state);
+    p.lse_off = static_cast<long long>(B) * Nq * H * 32;
+    p.rank = rank; p.G = G; p.B = B; p.H = H; p.Nq = Nq;
+    const long long total = static_cast<long long>(B) * Nq * H * 8;
+    if (scatter < 0) scatter = G > 2;   // measured: two handshakes cost more than reading one whole remote record
+    if (scatter) {
+        const long long chunk = ((total + G - 1) / G + 31) / 32 * 32;   // whole warps: full 256 / 512-byte stores
+        p.t_begin = chunk * rank < total ? chunk * rank : total;
+        p.t_end = chunk * (rank + 1) < total ? chunk * (rank + 1) : total;
+    } else {
+        p.t_begin = 0;
+        p.t_end = total;
+        p.ctx[0] = ctx[rank];   // the only context this mode writes
+    }
+    long long blocks = (p.t_end - p.t_begin + 255) / 256;
+    const long long cap = static_cast<long long>(device_sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;   // a rank without rows still takes part in the handshakes
+    const int nb = static_cast<int>(blocks);
+    if (o_dtype == CMT_BF16) {
+        if (scatter) lse_merge_peer_kernel<true, true><<<nb, 256, 0, stream>>>(p);
+        else lse_merge_peer_kernel<true, false><<<nb, 256, 0, stream>>>(p);
+    } else {
+        if (scatter) lse_merge_peer_kernel<false, true><<<nb, 256, 0, stream>>>(p);
+        else lse_merge_peer_kernel<false, false><<<nb, 256, 0, stream>>>(p);
+    }
+    CMT_LAUNCH_CHECK("cmt_lse_merge_peer");
+    return CMT_OK;
+}
+
 }  // namespace cmt

@@ -67,6 +67,8 @@ int launch_nchw_to_padded_nhwc(const void* x, void* out, int B, int C, int H, in
 int launch_coop_max(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
 int launch_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G,
                      int B, int H, int Nq, long long o_gstride, long long lse_gstride, int o_dtype, cudaStream_t stream);
+int launch_lse_merge_peer(const void* const* records, void* const* ctx, void* const* arrive, void* state, int rank, int G,
+                          int B, int H, int Nq, int o_dtype, int scatter, cudaStream_t stream);
 // norm_kernels.cu
 int launch_add_layernorm(const float* x, const float* r, const float* gamma, const float* beta, float eps, int M, int C,
                          float* y, const float* gamma2, const float* beta2, float* y2, const float* add, void* ylp,

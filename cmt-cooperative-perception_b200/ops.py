@@ -499,6 +499,25 @@ def lse_merge_packed(parts, G, B, Nq, H, o_dtype=torch.bfloat16):
     return o
 
 
+def lse_merge_peer(record_ptrs, ctx_ptrs, arrive_ptrs, state_ptr, rank, B, Nq, H, device, o_dtype=torch.bfloat16, scatter=-1):
+    """Exchange + merge + redistribution of the KV-token split in one kernel over peer memory (cmt_lse_merge_peer):
+    record_ptrs / ctx_ptrs / arrive_ptrs are the G ranks' device addresses (ints) of this exchange's packed record, of
+    the context buffer and of the counters, all mapped into this process (parallel.PeerExchange).  Collective over the
+    group; the merged context is in this rank's context buffer when the kernel has run.  scatter: 1 = each rank merges
+    1/G of the rows and stores them to all ranks, 0 = each rank merges all rows for itself, -1 = by group size."""
+    G = len(record_ptrs)
+    assert len(arrive_ptrs) == G and len(ctx_ptrs) == G and 0 <= rank < G
+    recs = (ctypes.c_void_p * G)(*record_ptrs)
+    ctxs = (ctypes.c_void_p * G)(*ctx_ptrs)
+    arrs = (ctypes.c_void_p * G)(*arrive_ptrs)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        rc = lib.cmt_lse_merge_peer(recs, ctxs, arrs, ctypes.c_void_p(state_ptr), rank, G, B, H, Nq, _dt(o_dtype), int(scatter),
+                                    ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _lib.check(rc, "cmt_lse_merge_peer")
+    _count()
+
+
 def coop_max(a, b):
     """max(nan_to_num(a), nan_to_num(b)) (cmt_head_coop.py:358,383-389)."""
     a = _cuda(a, "a", torch.float32)

@@ -9,6 +9,8 @@
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -51,6 +53,66 @@ def gather_packed(record: torch.Tensor, group=None):
     out = torch.empty((world * record.numel(),), dtype=record.dtype, device=record.device)
     dist.all_gather_into_tensor(out, record, group=group)
     return out
+
+
+class PeerExchange:
+    """Peer-mapped buffers for the fused exchange + merge of the KV-token split (ops.lse_merge_peer), one allocation per
+    rank from torch's symmetric memory, every rank's mapped into every process of the group over NVLink:
+    `n_slots` packed (O | LSE) records of B*Nq*H*32 + B*H*Nq fp32, `n_slots` context buffers of B*Nq*H*32 (room for
+    fp32), then 64 control words {record counters [8], context counters [8], exchange number, finished blocks, ...}.
+    Nothing here touches the data path: `record(i)` hands out views for the attention kernel to write, `merge(i)`
+    launches the one kernel that announces, waits, merges this rank's share of the rows from all ranks' records and
+    stores it into all ranks' context buffers.  Consecutive exchanges must use different slots (n_slots >= 2 and
+    slot = decoder layer does that, also across forwards and CUDA-graph replays); the returned context is a view of
+    slot i's buffer, valid until the next exchange on that slot."""
+
+    CTRL_WORDS = 64
+
+    def __init__(self, group, device, B: int, Nq: int, H: int, n_slots: int):
+        import torch.distributed._symmetric_memory as symm
+        assert n_slots >= 2, "two consecutive exchanges must not share a record slot"
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        assert self.world <= 8
+        self.device = torch.device(device)
+        self.shape = (B, Nq, H)
+        self.n_o, self.n_l = B * Nq * H * 32, B * H * Nq
+        self.n_rec = self.n_o + self.n_l
+        assert self.n_rec % 4 == 0 and self.n_o % 4 == 0
+        self.n_slots = n_slots
+        self.scatter = int(os.environ.get("CMT_PEER_SCATTER", "-1"))   # debugging: force one of the two kernel modes (same on every rank)
+        self.ctx_off = n_slots * self.n_rec                     # in fp32 words
+        self.ctrl_off = self.ctx_off + n_slots * self.n_o
+        self.buf = symm.empty(self.ctrl_off + self.CTRL_WORDS, dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        torch.cuda.current_stream(self.device).synchronize()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(self.ptrs) == self.world and self.ptrs[self.rank] == self.buf.data_ptr()
+        self.arrive_ptrs = [p + self.ctrl_off * 4 for p in self.ptrs]
+        self.state_ptr = self.ptrs[self.rank] + (self.ctrl_off + 16) * 4
+        dist.barrier(self.group)   # every rank's counters are zero before anyone announces
+
+    def matches(self, B, Nq, H, n_slots):
+        return self.shape == (B, Nq, H) and self.n_slots >= n_slots
+
+    def record(self, slot: int):
+        """Views (record, o [B,Nq,H*32], lse [B,H,Nq]) of this rank's slot."""
+        B, Nq, H = self.shape
+        rec = self.buf[slot * self.n_rec:(slot + 1) * self.n_rec]
+        return rec, rec[:self.n_o].view(B, Nq, H * 32), rec[self.n_o:].view(B, H, Nq)
+
+    def merge(self, slot: int, o_dtype=torch.bfloat16):
+        from . import ops
+        B, Nq, H = self.shape
+        roff, coff = slot * self.n_rec * 4, (self.ctx_off + slot * self.n_o) * 4
+        ops.lse_merge_peer([p + roff for p in self.ptrs], [p + coff for p in self.ptrs], self.arrive_ptrs, self.state_ptr,
+                           self.rank, B, Nq, H, self.device, o_dtype, self.scatter)
+        ctx = self.buf[self.ctx_off + slot * self.n_o:self.ctx_off + (slot + 1) * self.n_o]
+        if o_dtype == torch.float32:
+            return ctx.view(B, Nq, H * 32)
+        return ctx.view(o_dtype)[:self.n_o].view(B, Nq, H * 32)
 
 
 def merge_partials_reference(o_all: torch.Tensor, l_all: torch.Tensor, num_heads: int):

@@ -32,7 +32,8 @@ class KVCache:
     query maxima it lets the attention kernel use a static softmax shift (ops.cross_attn).
     """
 
-    def __init__(self, k, vt, n_kv, group=None, k_norm2=None):
+    def __init__(self, k, vt, n_kv, group=None, k_norm2=None, peer=None):
+        self.peer = peer      # callable (B, Nq, H, device) -> parallel.PeerExchange: the layer's exchange + merge as one kernel over peer memory; None: NCCL all-gather
         self.k = k
         self.vt = vt
         self.k_norm2 = k_norm2
@@ -185,14 +186,18 @@ class FlashMHA(nn.Module):
         import torch.distributed as dist
         B, Nq, E = qp.shape
         H = self.num_heads
-        # the local partial goes straight into the packed (O | LSE) record this rank contributes to the layer's all-gather
-        record, o_part, lse = ops.packed_partial(B, Nq, H, qp.device)
+        # the local partial goes straight into the packed (O | LSE) record this rank contributes to the layer's exchange:
+        # a slot of the peer-mapped buffer (fused exchange + merge kernel) or a fresh buffer for the NCCL all-gather
+        peer = cache.peer(B, Nq, H, qp.device) if cache.peer is not None else None
+        record, o_part, lse = peer.record(layer) if peer is not None else ops.packed_partial(B, Nq, H, qp.device)
         if cache.n_kv > 0:
             ops.cross_attn(qp, cache.k, cache.vt, layer, o_dtype=torch.float32, out=o_part, lse_out=lse,
                            q_norm2=q_norm2, k_norm2=cache.k_norm2 if q_norm2 is not None else None)
         else:  # this rank holds no tokens: neutral element of the merge
             o_part.zero_()
             lse.fill_(float("-inf"))
+        if peer is not None:
+            return peer.merge(layer, _compute_dtype(self.precision))
         allrec = parallel.gather_packed(record, cache.group)
         ctx = ops.lse_merge_packed(allrec, dist.get_world_size(cache.group), B, Nq, H, o_dtype=_compute_dtype(self.precision))
         return ctx

@@ -61,6 +61,8 @@ class _CmtTransformerBase(nn.Module):
         self.cross = cross
         self.precision = "bf16"
         self.kv_split_group = None
+        self.kv_split_peer = False      # True: exchange + merge as one kernel over peer memory instead of NCCL all-gather + merge
+        self._peer = None
         self.use_fused_decoder = True  # False: module-by-module path (torch self-attention / LN / FFN)
         self._kv_w = None
         self._xp = None
@@ -135,7 +137,7 @@ class _CmtTransformerBase(nn.Module):
         L = len(self.decoder.layers)
         H = self.decoder.layers[0].attentions[-1].num_heads
         if hi <= lo:   # more ranks than token tiles: this rank contributes the neutral element of the merge
-            return KVCache(None, None, 0, group), None
+            return KVCache(None, None, 0, group, peer=self._peer_exchange if self.kv_split_peer else None), None
         # with the split, the gather kernel itself produces only the rank's rows: K1/K4/K2 all shard with the tokens
         if isinstance(x_bev, BevTokenSource):
             Hb, Wb = x_bev.shape[2], x_bev.shape[3]
@@ -161,17 +163,32 @@ class _CmtTransformerBase(nn.Module):
         kn2 = torch.zeros((B, L, H), dtype=torch.float32, device=xk.device) if dt == torch.bfloat16 else None
         k = ops.project_keys(xk, wk, bk, L, H, norm2_max=kn2)
         vt = ops.project_values_t(xv, wv, bv, L, H)
-        return KVCache(k, vt, hi - lo, group, k_norm2=kn2), xv
+        return KVCache(k, vt, hi - lo, group, k_norm2=kn2, peer=self._peer_exchange if (group is not None and self.kv_split_peer) else None), xv
 
-    def enable_kv_split(self, group=None):
+    def enable_kv_split(self, group=None, peer_memory=False):
         """Split the K/V token axis across the ranks of `group` (default: the WORLD group); every rank
-        must call forward with the SAME frames.  Pass `False` to switch back to frame sharding."""
+        must call forward with the SAME frames.  Pass `False` to switch back to frame sharding.
+        peer_memory=True: the per-layer exchange of (O | LSE) records and their merge run as ONE kernel that reads the
+        other ranks' records through NVLink (parallel.PeerExchange, cmt_lse_merge_peer) -- no NCCL call on the data path;
+        False: one NCCL all-gather per layer + cmt_lse_merge."""
         if group is False:
             self.kv_split_group = None
+            self.kv_split_peer = False
+            self._peer = None
             return self
         import torch.distributed as dist
         self.kv_split_group = group if group is not None else dist.group.WORLD
+        self.kv_split_peer = bool(peer_memory)
         return self
+
+    def _peer_exchange(self, B, Nq, H, device):
+        """The peer-mapped record buffers for this shape (allocated collectively on first use: every rank of the group
+        reaches this point with the same shapes; not inside a CUDA-graph capture -- run one eager forward first)."""
+        L = max(2, len(self.decoder.layers))
+        if self._peer is None or not self._peer.matches(B, Nq, H, L):
+            from .. import parallel
+            self._peer = parallel.PeerExchange(self.kv_split_group, device, B, Nq, H, L)
+        return self._peer
 
     def decode_nodes(self, caches, query_embed, attn_masks=None):
         """One decoder pass over several nodes' frames (query_embed [sum B_i, Nq, C], caches[i] covering B_i frames) when

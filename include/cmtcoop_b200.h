@@ -191,6 +191,23 @@ int cmt_cross_attn_fwd(const void* q, const void* k, const void* vt, void* o, fl
 int cmt_lse_merge(const float* o_parts, const float* lse_parts, void* o, float* lse, int G, int B,
                   int H, int Nq, int64_t o_gstride, int64_t lse_gstride, int o_dtype, void* stream);
 
+/* The same merge fused with its exchange over peer memory (NVLink / NVSwitch), replacing the NCCL all-gather of the
+ * KV-token split.  records[g] / ctx[g] / arrive[g] are HOST arrays of G <= 8 device pointers, all into memory mapped
+ * into every rank of the group (the caller maps it, e.g. torch symmetric memory): rank g's packed (O | LSE) record of
+ * this exchange -- o [B,Nq,H*32] fp32 followed by lse [B,H,Nq] fp32 --, rank g's context buffer [B,Nq,H*32] (o_dtype)
+ * and rank g's block of 16 uint32 counters; `state` points at two uint32 {exchange number, finished blocks} in LOCAL
+ * memory; counters and state are zero before the first exchange.  The kernel announces the local record to all ranks,
+ * waits for theirs, merges this rank's 1/G of the rows straight from the G records (remote ones read through NVLink),
+ * stores them into EVERY rank's context buffer, and returns once all ranks' rows have landed in ctx[rank]
+ * (scatter = 1: NVLink carries (G-1)/G of a record in and of a context out per rank; two handshakes).  scatter = 0: every
+ * rank merges ALL rows from the G records into ctx[rank] only (G - 1 records in, one handshake); scatter < 0 picks by
+ * group size (0 for G <= 2).  Every rank must pass the same mode.
+ * Collective: every rank of the group calls it once per exchange, in the same order; two consecutive exchanges must
+ * use different record buffers; a context buffer may be reused by the next exchange once its local reader is ahead of
+ * this call in the stream.  A rank that does not arrive within ~30 s traps. */
+int cmt_lse_merge_peer(const void* const* records, void* const* ctx, void* const* arrive, void* state, int rank, int G,
+                       int B, int H, int Nq, int o_dtype, int scatter, void* stream);
+
 /* ---- decoder small ops: fused residual add + LayerNorm --------------------------------
  * One launch for `query = norm(identity + attn_out)` of mmcv BaseTransformerLayer (post-norm order
  * self_attn, norm, cross_attn, norm, ffn, norm) plus PETRTransformerDecoder's shared post_norm

@@ -1,5 +1,6 @@
 """Two-GPU checks (skipped on a single-GPU box): the KV-token split with NCCL all-gather + LSE merge
-must reproduce the single-GPU forward, and frame sharding needs no collective."""
+must reproduce the single-GPU forward, the peer-memory exchange must reproduce the all-gather path bit for bit, and
+frame sharding needs no collective."""
 import os
 import socket
 
@@ -42,9 +43,25 @@ def _worker(rank, world, port, q_out):
             head.transformer.enable_kv_split()
             n0 = ops.launch_count()
             split = head.forward_single(x, xi, inputs["img_metas"])
+            # the same split with the exchange + merge as one kernel over peer memory: same arithmetic in the same
+            # order as all-gather + merge, so the outputs must be bit-identical -- three forwards, so record slots and
+            # exchange numbers wrap around
+            head.transformer.enable_kv_split(peer_memory=True)
+            peer_same = True
+            for _ in range(3):
+                peer = head.forward_single(x, xi, inputs["img_metas"])
+                peer_same = peer_same and all(torch.equal(peer[0][n], split[0][n]) for n in split[0])
+            # ... and in the kernel's other mode (each rank merges 1/G of the rows and stores them to every rank: what
+            # groups of more than two ranks run)
+            head.transformer._peer.scatter = 1
+            for _ in range(2):
+                peer = head.forward_single(x, xi, inputs["img_metas"])
+                peer_same = peer_same and all(torch.equal(peer[0][n], split[0][n]) for n in split[0])
             head.transformer.enable_kv_split(False)
         torch.cuda.synchronize()
         worst = max(O.rel_l2(split[0][n].float().cpu(), full[0][n].float().cpu()) for n in full[0])
+        if not peer_same:
+            worst = float("inf")
         # the rank's share of the token axis really is a share: gather / conv epilogue / projections saw only its rows
         n_kv = 37 * 37 + 3 * 7 * 13
         lo, hi = head.transformer.kv_token_range(n_kv)
