@@ -229,6 +229,65 @@ def test_coop_max_and_lse_merge():
     assert torch.allclose(got_l.cpu(), torch.logsumexp(lse, 0), atol=1e-5)
 
 
+def _peer_group_on_one_gpu(G, B, Nq, H, seed):
+    """G emulated ranks in ordinary device memory of ONE GPU: per rank a packed (O | LSE) record, a context buffer and 64
+    control words -- what parallel.PeerExchange lays out in symmetric memory."""
+    g = torch.Generator().manual_seed(seed)
+    n_o, n_l = B * Nq * H * 32, B * H * Nq
+    o = torch.randn(G, B, Nq, H * 32, generator=g)
+    lse = torch.randn(G, B, H, Nq, generator=g) * 3
+    lse[0, 0, 0, :3] = float("-inf")                                   # a rank with no keys for these rows
+    bufs = []
+    for r in range(G):
+        buf = torch.zeros(n_o + n_l + n_o + 64, dtype=torch.float32, device=DEV)
+        buf[:n_o] = o[r].reshape(-1).to(DEV)
+        buf[n_o:n_o + n_l] = lse[r].reshape(-1).to(DEV)
+        bufs.append(buf)
+    w = torch.nan_to_num(torch.softmax(lse, 0), nan=0.0)               # G = 1: no rank has keys for those rows -> zeros
+    want = (o.view(G, B, Nq, H, 32) * w.permute(0, 1, 3, 2).unsqueeze(-1)).sum(0).reshape(B, Nq, H * 32)
+    return bufs, n_o, n_l, want
+
+
+@pytest.mark.parametrize("scatter", [0, 1])
+def test_lse_merge_peer_single_rank(scatter):
+    """The peer-memory exchange + merge kernel with a group of one (plain device memory): both handshakes with itself,
+    the merge of one record is the identity, the exchange number advances across launches."""
+    B, Nq, H = 2, 37, 8
+    bufs, n_o, n_l, want = _peer_group_on_one_gpu(1, B, Nq, H, 3)
+    base = bufs[0].data_ptr()
+    for it in range(3):
+        ops.lse_merge_peer([base], [base + (n_o + n_l) * 4], [base + (2 * n_o + n_l) * 4], base + (2 * n_o + n_l + 16) * 4,
+                           0, B, Nq, H, torch.device(DEV), torch.float32, scatter)
+        torch.cuda.synchronize()
+        ctrl = bufs[0][2 * n_o + n_l:].view(torch.int32)
+        assert int(ctrl[16]) == it + 1 and int(ctrl[17]) == 0 and int(ctrl[0]) == it + 1
+        assert int(ctrl[8]) == (it + 1 if scatter else 0)
+    got = bufs[0][n_o + n_l:2 * n_o + n_l].view(B, Nq, H * 32)
+    assert _rel(got, want) < 1e-6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CMT_TEST_PEER_EMULATION") != "1",
+                    reason="opt-in: G kernels of one GPU wait for each other -- needs them co-resident (never under a "
+                           "serialising profiler); the real multi-process check is tests/test_gpu_multi.py")
+@pytest.mark.parametrize("G,scatter", [(2, 0), (3, 1), (8, 1)])
+def test_lse_merge_peer_emulated_group(G, scatter):
+    B, Nq, H = 2, 37, 8
+    bufs, n_o, n_l, want = _peer_group_on_one_gpu(G, B, Nq, H, 5 + G)
+    bases = [b.data_ptr() for b in bufs]
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    torch.cuda.synchronize()
+    for it in range(2):
+        for r in range(G):
+            with torch.cuda.stream(streams[r]):
+                ops.lse_merge_peer(bases, [p + (n_o + n_l) * 4 for p in bases], [p + (2 * n_o + n_l) * 4 for p in bases],
+                                   bases[r] + (2 * n_o + n_l + 16) * 4, r, B, Nq, H, torch.device(DEV), torch.bfloat16, scatter)
+        torch.cuda.synchronize()
+    for r in range(G):
+        got = bufs[r][n_o + n_l:2 * n_o + n_l].view(torch.bfloat16)[:n_o].view(B, Nq, H * 32).float()
+        assert _rel(got, want) < 4e-3, r                                  # bf16 output rounding
+        assert torch.equal(got, bufs[0][n_o + n_l:2 * n_o + n_l].view(torch.bfloat16)[:n_o].view(B, Nq, H * 32).float())
+
+
 # ------------------------------------------------------------------------------------------
 GEMM_CASES = [
     # M, N, K, relu, bias, alpha
