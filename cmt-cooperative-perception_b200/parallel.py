@@ -55,6 +55,21 @@ def gather_packed(record: torch.Tensor, group=None):
     return out
 
 
+def peer_layout(B: int, Nq: int, H: int, n_slots: int, head_dim: int = 32, ctrl_words: int = 64):
+    """Word (4-byte) offsets inside one rank's peer-mapped allocation: `n_slots` packed (O | LSE) records, `n_slots`
+    context buffers (room for fp32), then the control words {record counters [8], context counters [8], exchange number,
+    finished blocks, ...}.  Every record and context buffer starts on a 16-byte boundary (the kernel moves 128-bit
+    words)."""
+    n_o, n_l = B * Nq * H * head_dim, B * H * Nq
+    n_rec = n_o + n_l
+    if n_rec % 4 or n_o % 4:
+        raise ValueError("peer exchange: B*Nq*H must be a multiple of 4 (16-byte aligned records)")
+    ctx_off = n_slots * n_rec
+    ctrl_off = ctx_off + n_slots * n_o
+    return dict(n_o=n_o, n_l=n_l, n_rec=n_rec, ctx_off=ctx_off, ctrl_off=ctrl_off, total=ctrl_off + ctrl_words,
+                state_word=ctrl_off + 16)
+
+
 class PeerExchange:
     """Peer-mapped buffers for the fused exchange + merge of the KV-token split (ops.lse_merge_peer), one allocation per
     rank from torch's symmetric memory, every rank's mapped into every process of the group over NVLink:
@@ -77,14 +92,12 @@ class PeerExchange:
         assert self.world <= 8
         self.device = torch.device(device)
         self.shape = (B, Nq, H)
-        self.n_o, self.n_l = B * Nq * H * 32, B * H * Nq
-        self.n_rec = self.n_o + self.n_l
-        assert self.n_rec % 4 == 0 and self.n_o % 4 == 0
+        lay = peer_layout(B, Nq, H, n_slots, ctrl_words=self.CTRL_WORDS)
+        self.n_o, self.n_l, self.n_rec = lay["n_o"], lay["n_l"], lay["n_rec"]
         self.n_slots = n_slots
         self.scatter = int(os.environ.get("CMT_PEER_SCATTER", "-1"))   # debugging: force one of the two kernel modes (same on every rank)
-        self.ctx_off = n_slots * self.n_rec                     # in fp32 words
-        self.ctrl_off = self.ctx_off + n_slots * self.n_o
-        self.buf = symm.empty(self.ctrl_off + self.CTRL_WORDS, dtype=torch.float32, device=self.device)
+        self.ctx_off, self.ctrl_off = lay["ctx_off"], lay["ctrl_off"]   # in fp32 words
+        self.buf = symm.empty(lay["total"], dtype=torch.float32, device=self.device)
         self.buf.zero_()
         torch.cuda.current_stream(self.device).synchronize()
         self.handle = symm.rendezvous(self.buf, self.group)

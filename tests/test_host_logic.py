@@ -104,6 +104,25 @@ def test_kv_split_ranges_partition_the_tokens(n, world):
 
 
 @settings(max_examples=200, deadline=None)
+@given(B=st.integers(1, 16), Nq=st.integers(1, 1200), H=st.integers(1, 8), slots=st.integers(2, 8))
+def test_peer_exchange_layout(B, Nq, H, slots):
+    """Buffers of the peer-memory exchange (parallel.PeerExchange): records, contexts and control words tile the
+    allocation without overlap, and everything the kernel moves in 128-bit words is 16-byte aligned."""
+    if (B * Nq * H) % 4:
+        with pytest.raises(ValueError):
+            parallel.peer_layout(B, Nq, H, slots)
+        return
+    lay = parallel.peer_layout(B, Nq, H, slots)
+    assert lay["n_rec"] == B * Nq * H * 32 + B * H * Nq
+    rec = [(i * lay["n_rec"], (i + 1) * lay["n_rec"]) for i in range(slots)]
+    ctx = [(lay["ctx_off"] + i * lay["n_o"], lay["ctx_off"] + (i + 1) * lay["n_o"]) for i in range(slots)]
+    spans = rec + ctx + [(lay["ctrl_off"], lay["total"])]
+    assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert all(lo % 4 == 0 for lo, _ in spans)                       # 4-byte words -> 16-byte alignment
+    assert lay["ctrl_off"] + 16 == lay["state_word"] < lay["total"]
+
+
+@settings(max_examples=200, deadline=None)
 @given(n=st.integers(0, 1000), world=st.integers(1, 16))
 def test_frame_shards_partition_the_batch(n, world):
     ranges = [parallel.shard_frames(n, r, world) for r in range(world)]
