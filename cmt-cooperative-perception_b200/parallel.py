@@ -55,6 +55,38 @@ def gather_packed(record: torch.Tensor, group=None):
     return out
 
 
+def token_rows_copy_plan(bev_shape, img_shape, B: int, lo: int, hi: int, halo: int = 0):
+    """Which parts of the NCHW feature maps does a rank of the KV-token split read?  Tokens are the concatenation of
+    the BEV positions (y * W + x) and the image positions (v * h * w + y * w + x) of a frame; the rank owns [lo, hi).
+    Returns {"pts": [...], "img": [...]}: rectangles (offset, pitch, width, height) in ELEMENTS of the contiguous
+    [B, C, H, W] / [B*V, C, h, w] tensors -- `height` runs of `width` elements, `pitch` apart, starting at `offset` --
+    that cover every map row holding one of the rank's tokens (whole rows; `halo` extra BEV rows on both sides for the
+    3x3 shared_conv).  bev_shape / img_shape: tensor shapes or None."""
+    plan = {"pts": [], "img": []}
+    n_bev = 0
+    if bev_shape is not None:
+        Bb, C, H, W = bev_shape
+        assert Bb == B
+        n_bev = H * W
+        a, b = min(lo, n_bev), min(hi, n_bev)
+        if b > a:
+            y0, y1 = max(0, a // W - halo), min(H, (b + W - 1) // W + halo)
+            plan["pts"].append((y0 * W, H * W, (y1 - y0) * W, B * C))
+    if img_shape is not None:
+        BV, C, h, w = img_shape
+        V = BV // B
+        assert V * B == BV
+        a, b = max(lo, n_bev) - n_bev, min(max(hi, n_bev) - n_bev, V * h * w)
+        if b > a:
+            va, vb = a // (h * w), (b - 1) // (h * w)
+            for v in range(va, vb + 1):
+                r0 = (a - v * h * w) // w if v == va else 0
+                r1 = (b - v * h * w + w - 1) // w if v == vb else h
+                for f in range(B):
+                    plan["img"].append((((f * V + v) * C) * h * w + r0 * w, h * w, (r1 - r0) * w, C))
+    return plan
+
+
 def peer_layout(B: int, Nq: int, H: int, n_slots: int, head_dim: int = 32, ctrl_words: int = 64):
     """Word (4-byte) offsets inside one rank's peer-mapped allocation: `n_slots` packed (O | LSE) records, `n_slots`
     context buffers (room for fp32), then the control words {record counters [8], context counters [8], exchange number,

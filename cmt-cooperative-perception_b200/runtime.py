@@ -60,7 +60,7 @@ class numa_local_to_gpu:
 
 class PipelinedRunner:
     def __init__(self, head, img_metas, example_inputs: dict, device, use_cuda_graph: bool = False,
-                 keep_results: bool = True):
+                 keep_results: bool = True, partial_upload=None):
         """example_inputs: {name: pinned CPU tensor} with the feature tensors `forward_single` takes
         (pts_feats / img_feats, or the four vehicle_/infrastructure_ entries for the coop heads); fp32, bf16 or
         fp16 -- the gather kernel rounds every feature to the compute dtype on arrival, so 16-bit features halve
@@ -68,7 +68,10 @@ class PipelinedRunner:
         use_cuda_graph: replay one captured forward per device input slot instead of launching eagerly.
         keep_results: `run` returns every batch's outputs as ordinary CPU tensors (copied out of the two pinned
         staging buffers before those are reused); False keeps only the staging buffers (results of the last two
-        batches), for callers that consume results through `on_result`."""
+        batches), for callers that consume results through `on_result`.
+        partial_upload: under the KV-token split a rank reads only the map rows that hold its tokens, so only those
+        rows are copied to the device (a few strided cudaMemcpy2DAsync per tensor, parallel.token_rows_copy_plan); the rest of
+        the device buffers is never read.  None = do so whenever the split is enabled on a non-cooperative head."""
         self.head = head
         self.metas = img_metas
         self.dev = torch.device(device)
@@ -87,6 +90,13 @@ class PipelinedRunner:
         self.h2d_bytes = int(sum(example_inputs[k].numel() * example_inputs[k].element_size() for k in self.keys))
         self.d2h_bytes = 0
         self.graphs = None
+        self.copy_plan = None
+        tr = getattr(head, "transformer", None)
+        if partial_upload is None:
+            partial_upload = (tr is not None and getattr(tr, "kv_split_group", None) is not None and not self.coop
+                              and set(self.keys) <= {"pts_feats", "img_feats"})
+        if partial_upload:
+            self._plan_partial_upload(example_inputs)
         if use_cuda_graph:
             for slot in range(2):     # the graphs read the slot buffers in place: give them defined contents first
                 for k in self.keys:
@@ -101,12 +111,42 @@ class PipelinedRunner:
                                             g("vehicle_img_feats"), g("infrastructure_img_feats"), self.metas)
         return self.head.forward_single(g("pts_feats"), g("img_feats"), self.metas)
 
+    def _plan_partial_upload(self, example_inputs):
+        """Rectangles of the feature maps this rank's tokens live in (KV-token split)."""
+        import ctypes
+
+        from . import parallel
+        pts, img = example_inputs.get("pts_feats"), example_inputs.get("img_feats")
+        B = pts.shape[0] if pts is not None else len(self.metas)
+        n_kv = (pts.shape[2] * pts.shape[3] if pts is not None else 0) + \
+               ((img.shape[0] // B) * img.shape[2] * img.shape[3] if img is not None else 0)
+        lo, hi = self.head.transformer.kv_token_range(n_kv)
+        halo = 1 if (getattr(self.head, "apply_shared_conv", True) and getattr(self.head, "shared_conv", None) is not None) else 0
+        plan = parallel.token_rows_copy_plan(None if pts is None else tuple(pts.shape), None if img is None else tuple(img.shape),
+                                             B, lo, hi, halo)
+        self.copy_plan = {"pts_feats": plan["pts"], "img_feats": plan["img"]}
+        self._cudart = ctypes.CDLL("libcudart.so.12")      # the runtime torch has loaded
+        self._cudart.cudaMemcpy2DAsync.restype = ctypes.c_int
+        self._cudart.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                                   ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        self.h2d_bytes = int(sum(w * h * example_inputs[k].element_size() for k in self.keys for _, _, w, h in self.copy_plan[k]))
+
     def _enqueue_copy_in(self, slot, host_inputs):
         with torch.cuda.stream(self.s_in):
             if self._primed[slot]:
                 self.s_in.wait_event(self.ev_free[slot])   # the previous user of this slot has consumed it
             for k in self.keys:
-                self.dbuf[slot][k].copy_(host_inputs[k], non_blocking=True)
+                if self.copy_plan is None:
+                    self.dbuf[slot][k].copy_(host_inputs[k], non_blocking=True)
+                    continue
+                src, dst = host_inputs[k], self.dbuf[slot][k]
+                assert src.is_contiguous() and src.is_pinned() and src.shape == dst.shape and src.dtype == dst.dtype
+                esz = src.element_size()
+                for off, pitch, width, height in self.copy_plan[k]:
+                    rc = self._cudart.cudaMemcpy2DAsync(dst.data_ptr() + off * esz, pitch * esz, src.data_ptr() + off * esz,
+                                                        pitch * esz, width * esz, height, 1, self.s_in.cuda_stream)
+                    if rc != 0:
+                        raise RuntimeError(f"cudaMemcpy2DAsync failed with error {rc}")
             self.ev_in[slot].record(self.s_in)
 
     def _collect(self, slot):

@@ -103,6 +103,48 @@ def test_kv_split_ranges_partition_the_tokens(n, world):
     assert all(lo % parallel.KV_TILE == 0 or lo == n for lo, _ in ranges)
 
 
+@settings(max_examples=150, deadline=None)
+@given(B=st.integers(1, 3), H=st.integers(1, 9), W=st.integers(1, 9), V=st.integers(0, 3), h=st.integers(1, 5),
+       w=st.integers(1, 6), world=st.integers(1, 5), halo=st.integers(0, 1), data=st.data())
+def test_token_rows_copy_plan_covers_the_ranks_tokens(B, H, W, V, h, w, world, halo, data):
+    """The partial host->device hand-over of the KV-token split: applying the rank's rectangles to NaN-filled copies
+    reproduces every feature value of the rank's tokens (and the halo rows), whatever the split point."""
+    C = 2
+    n_bev, n_img = H * W, V * h * w
+    n_kv = n_bev + n_img
+    cut = sorted(data.draw(st.lists(st.integers(0, n_kv), min_size=world - 1, max_size=world - 1)))
+    bounds = [0] + cut + [n_kv]
+    rng = np.random.RandomState(H * 131 + W * 17 + V)
+    bev = rng.rand(B, C, H, W).astype(np.float32)
+    img = rng.rand(B * V, C, h, w).astype(np.float32) if V else None
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        plan = parallel.token_rows_copy_plan(bev.shape, None if img is None else img.shape, B, lo, hi, halo)
+        for name, src in (("pts", bev), ("img", img)):
+            if src is None:
+                assert not plan[name]
+                continue
+            dst = np.full(src.size, np.nan, np.float32)
+            flat = src.reshape(-1)
+            for off, pitch, width, height in plan[name]:
+                assert 0 < width <= pitch and off >= 0 and off + (height - 1) * pitch + width <= src.size
+                for i in range(height):
+                    dst[off + i * pitch: off + i * pitch + width] = flat[off + i * pitch: off + i * pitch + width]
+            dst = dst.reshape(src.shape)
+            if name == "pts":
+                tok = dst.reshape(B, C, n_bev)
+                a, b = min(lo, n_bev), min(hi, n_bev)
+                assert np.array_equal(tok[:, :, a:b], bev.reshape(B, C, n_bev)[:, :, a:b])
+                if b > a and halo:
+                    y0, y1 = max(0, a // W - 1), min(H, (b + W - 1) // W + 1)
+                    assert np.array_equal(dst[:, :, y0:y1], bev[:, :, y0:y1])
+            else:
+                tok = dst.reshape(B, V, C, h * w).transpose(0, 2, 1, 3).reshape(B, C, n_img)
+                want = img.reshape(B, V, C, h * w).transpose(0, 2, 1, 3).reshape(B, C, n_img)
+                a, b = max(lo, n_bev) - n_bev, max(hi, n_bev) - n_bev
+                assert np.array_equal(tok[:, :, a:b], want[:, :, a:b])
+
+
 @settings(max_examples=200, deadline=None)
 @given(B=st.integers(1, 16), Nq=st.integers(1, 1200), H=st.integers(1, 8), slots=st.integers(2, 8))
 def test_peer_exchange_layout(B, Nq, H, slots):
