@@ -125,6 +125,7 @@ class PipelinedRunner:
         plan = parallel.token_rows_copy_plan(None if pts is None else tuple(pts.shape), None if img is None else tuple(img.shape),
                                              B, lo, hi, halo)
         self.copy_plan = {"pts_feats": plan["pts"], "img_feats": plan["img"]}
+        self._plan_key = (n_kv, lo, hi)
         self._cudart = ctypes.CDLL("libcudart.so.12")      # the runtime torch has loaded
         self._cudart.cudaMemcpy2DAsync.restype = ctypes.c_int
         self._cudart.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
@@ -135,6 +136,11 @@ class PipelinedRunner:
         with torch.cuda.stream(self.s_in):
             if self._primed[slot]:
                 self.s_in.wait_event(self.ev_free[slot])   # the previous user of this slot has consumed it
+            if self.copy_plan is not None:
+                n_kv, lo, hi = self._plan_key
+                if self.head.transformer.kv_token_range(n_kv) != (lo, hi):
+                    raise RuntimeError("PipelinedRunner: the KV-token split changed after the partial upload was planned; "
+                                       "build a new runner")
             for k in self.keys:
                 if self.copy_plan is None:
                     self.dbuf[slot][k].copy_(host_inputs[k], non_blocking=True)
